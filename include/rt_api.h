@@ -1,0 +1,171 @@
+/* rt_api.h -- C ABI of librt_b200.so, the B200-native replacement for the reference's per-pixel path-tracing
+ * loop (metametamoon/raytracing-course-2024).
+ *
+ * The reference has no FFI layer: its seam is ONE Rust call,
+ *     pub fn render_scene(scene: &Scene) -> Vec<u8>            (src/rendering.rs:21, called at src/main.rs:55)
+ * fed by  gltf::import + convert_gltf_to_scene                  (src/main.rs:45-47, src/gltf_to_scene.rs:21-79)
+ * and followed by dump_rendered_to_ppm                          (src/main.rs:88-95).
+ * Every entry point below names the reference interface it replaces.  All signatures are plain C: pointers,
+ * sizes and PODs, no C++/torch types.  A Rust `rt-sys` crate binds these 1:1.
+ *
+ * Conventions: every function returns 0 on success or an RT_ERR_* code; rt_last_error() gives the message of the
+ * calling thread's last failure.  Nothing aborts the process (the reference panics instead: unwrap()/assert!).
+ * Host buffers are caller-owned.  An RtScene owns its host copy, its device copy and its streams until
+ * rt_scene_destroy.  There is NO CPU fallback: without a CUDA device every compute entry point fails with
+ * RT_ERR_CUDA.
+ */
+#ifndef RT_API_H
+#define RT_API_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define RT_API_VERSION 1
+
+enum {
+    RT_OK = 0,
+    RT_ERR_INVALID = 1,  /* bad argument (samples <= 0, width*height <= 0, null pointer, ...)            */
+    RT_ERR_IO = 2,       /* file could not be read / written                                           */
+    RT_ERR_FORMAT = 3,   /* glTF the reference would reject (todo!() at gltf_to_scene.rs:131-133,151-153) */
+    RT_ERR_CUDA = 4,     /* no device, or a CUDA call failed                                           */
+    RT_ERR_LIMIT = 5     /* scene exceeds a build-time limit (e.g. BVH deeper than the traversal stack)  */
+};
+
+typedef struct RtScene RtScene; /* opaque */
+
+/* The reference's `Scene` (src/scene.rs:22-39) flattened, in the reference's own numeric type (f64,
+ * src/geometry.rs:5) and in LOAD order (the order gltf_to_scene.rs:170-241 pushes primitives).  Only triangles
+ * exist at HEAD for glTF input (Shape3D::Triangle, identity rotation, zero position).  Materials are per
+ * primitive like scene.rs:13-20.  The BVHs of scene.rs:31,37 are NOT part of the description: rt_scene_create
+ * builds its own device BVH (node order is not observable through render_scene). */
+typedef struct RtSceneDesc {
+    int32_t width, height;            /* scene.rs:23-24                                                   */
+    int32_t samples;                  /* scene.rs:35                                                      */
+    int32_t ray_depth;                /* scene.rs:33 (6 for glTF scenes, gltf_to_scene.rs:73)             */
+    double bg_color[3];               /* scene.rs:25                                                      */
+    double camera_position[3];        /* scene.rs:26                                                      */
+    double camera_forward[3];         /* scene.rs:27                                                      */
+    double camera_right[3];           /* scene.rs:28                                                      */
+    double camera_up[3];              /* scene.rs:29                                                      */
+    double camera_fov_x, camera_fov_y; /* radians, scene.rs:30-31                                         */
+    int32_t n_tris;
+    int32_t reserved0;
+    const double* tri_v;              /* n_tris x 9: a, b, c                     (geometry.rs:31-38)      */
+    const double* tri_n;              /* n_tris x 9: a_norm, b_norm, c_norm                               */
+    const double* tri_material;       /* n_tris x 5: base_color rgb, metallic_factor, metallic_roughness (scene.rs:6-11) */
+    const double* tri_emission;       /* n_tris x 3                                (scene.rs:19)          */
+} RtSceneDesc;
+
+typedef struct RtSceneInfo {
+    int32_t n_tris, n_lights, n_materials;
+    int32_t n_nodes;                  /* inner (child-pair) nodes of the device BVH                       */
+    int32_t n_leaves, bvh_depth, max_leaf_size;
+    int32_t bvh_validate_failures;    /* validate_bvh (bvh.rs:299-322) restated on the flattened BVH      */
+    int32_t scene_in_shared_memory;   /* 1 if the render kernels stage the whole scene in shared memory   */
+    int32_t device;
+    int64_t device_bytes;             /* bytes of the device-resident scene                               */
+} RtSceneInfo;
+
+typedef struct RtRenderParams {
+    uint64_t seed;                    /* Philox key; the reference seeds xoshiro per row (rendering.rs:50-51) */
+    int32_t sample_begin, sample_end; /* this call renders samples [begin,end) of [0,samples); 0,0 = all  */
+    int32_t max_attempts;             /* cap of the rejection loop rendering.rs:102-110 (0 = default 64)  */
+    int32_t collect_stats;            /* 1: run the instrumented kernel and fill the work counters         */
+    int32_t kernel_variant;           /* 0 = auto; >0 selects a specific kernel build (benchmarks)        */
+    int32_t reserved[3];
+} RtRenderParams;
+
+typedef struct RtStats {
+    uint64_t samples;                 /* camera paths started                                              */
+    uint64_t segments;                /* nearest-hit queries (rendering.rs:96)                            */
+    uint64_t vertices;                /* hits that ran the sampling loop                                   */
+    uint64_t attempts;                /* iterations of the rejection loop rendering.rs:102-110             */
+    uint64_t node_tests;              /* ray/AABB slab tests                                               */
+    uint64_t tri_tests;               /* ray/triangle tests in nearest-hit queries                         */
+    uint64_t light_tri_tests;         /* ray/triangle tests of the light pdf (distributions.rs:160-184)    */
+    uint64_t attempt_cap_hits;        /* paths cut because max_attempts was reached (reference: spins)     */
+    uint64_t nonfinite_samples;       /* samples dropped because their radiance was NaN/Inf                */
+    uint64_t kernel_launches;         /* CUDA kernels launched by this call                                */
+    double   kernel_ms;               /* device time of the render kernels (CUDA events)                   */
+    double   total_ms;                /* device time of the whole call incl. copies (CUDA events)          */
+} RtStats;
+
+/* ---- error reporting ------------------------------------------------------------------------------------ */
+const char* rt_last_error(void);
+int rt_api_version(void);
+int rt_device_count(int32_t* count);
+
+/* ---- scene ingest ---------------------------------------------------------------------------------------- */
+/* Replaces gltf::import(path) + convert_gltf_to_scene(&gltf,&buffers,w,h,samples)  (main.rs:45-47,
+ * gltf_to_scene.rs:21-79) including create_bvh_tree (gltf_to_scene.rs:72,77): parses the .gltf/.bin on the
+ * host, builds the device BVH and uploads everything to `device`.  device = -1 creates a HOST-ONLY scene (loader
+ * and BVH inspection through rt_scene_get_desc / rt_scene_info / rt_scene_get_bvh); every compute entry point
+ * fails on it with RT_ERR_CUDA. */
+int rt_scene_load_gltf(const char* path, int32_t width, int32_t height, int32_t samples, int32_t device, RtScene** out);
+/* Replaces constructing a `Scene` by hand (scene.rs:22-39): a caller that already has the flat primitives
+ * (e.g. the Rust host after its own convert_gltf_to_scene) hands them over; arrays are copied. */
+int rt_scene_create(const RtSceneDesc* desc, int32_t device, RtScene** out);
+void rt_scene_destroy(RtScene* scene);
+/* Host-side view of the flat scene (pointers stay valid until rt_scene_destroy) -- what the loader produced. */
+int rt_scene_get_desc(const RtScene* scene, RtSceneDesc* out);
+int rt_scene_info(const RtScene* scene, RtSceneInfo* out);
+/* Change samples / image size without re-uploading geometry (main.rs:39-41 are per-run arguments). */
+int rt_scene_set_frame(RtScene* scene, int32_t width, int32_t height, int32_t samples);
+/* Device BVH dump for the containment check (bvh.rs:299-322).  nodes: n_nodes x 14 floats =
+ * child0 min xyz,max xyz, child1 min xyz,max xyz, child0 ref, child1 ref (refs as floats of the int encoding:
+ * >= 0 inner node index, < 0 leaf ~((first << 3) | (count-1))); tri_order: n_tris original triangle ids. */
+int rt_scene_get_bvh(const RtScene* scene, float* nodes, int32_t* tri_order);
+
+/* ---- the hot path ---------------------------------------------------------------------------------------- */
+/* Replaces render_scene(&scene) -> Vec<u8>  (rendering.rs:21-69): W*H*3 bytes, RGB8, row-major, row 0 = top.
+ * Host output buffer; the device->host copy is inside the call. */
+int rt_render(RtScene* scene, const RtRenderParams* params, uint8_t* rgb_out, RtStats* stats);
+/* Same estimator, but returns the per-pixel mean linear radiance before color_to_pixel (W*H*3 floats, host).
+ * Exists for the statistical parity tests. */
+int rt_render_linear(RtScene* scene, const RtRenderParams* params, float* rgb_linear_out, RtStats* stats);
+/* Multi-GPU building block (one process per GPU): ADDS the radiance SUMS of samples [begin,end) into a
+ * device-resident accumulator of W*H*4 floats (rgb + sample count) on `stream` (a cudaStream_t, may be null).
+ * The caller reduces the accumulators across ranks (NCCL sum) and resolves on one rank. */
+int rt_render_accumulate_device(RtScene* scene, const RtRenderParams* params, float* accum_dev, void* stream, RtStats* stats);
+/* color_to_pixel (rendering.rs:250-262) over a device accumulator: mean = rgb / count, ACES, gamma 1/2.2,
+ * round, saturating u8.  rgb_dev: W*H*3 bytes on the device. */
+int rt_resolve_device(const float* accum_dev, int32_t width, int32_t height, uint8_t* rgb_dev, void* stream);
+
+/* Nearest-hit query of the finite-primitive BVH for caller-supplied rays: replaces
+ * interesect_with_bvh_nearest_point (bvh.rs:231-247) for n rays (rays: n x 6 doubles, origin + direction).
+ * precision 32 = the production FP32 traversal the renderer uses; 64 = same traversal with f64 triangle tests.
+ * tri_id = ORIGINAL (load-order) triangle index or -1; t = hit distance (inf on miss). */
+int rt_trace_primary(RtScene* scene, const double* rays, int64_t n, int32_t precision, int32_t* tri_id, double* t);
+/* Camera rays of get_ray_to_pixel (rendering.rs:71-84) for explicit jitter: xy n x 2 ints, xi n x 2 doubles ->
+ * rays n x 6 doubles, computed on the device in FP32 exactly as the render kernel does. */
+int rt_primary_rays(RtScene* scene, const int32_t* xy, const double* xi, int64_t n, double* rays_out);
+
+/* ---- device unit functions (parity tests of the device samplers / BRDF against the oracle) --------------- */
+enum {
+    RT_FN_BRDF = 1,          /* in: l3 n3 v3 base3 metallic rough (14)   out: rgb (3)   rendering.rs:133-155     */
+    RT_FN_PDF_COSINE = 2,    /* in: n3 l3 (6)                            out: 1         distributions.rs:65-67   */
+    RT_FN_PDF_VNDF = 3,      /* in: n3 l3 v3 rough (10)                  out: 1         distributions.rs:276-297 */
+    RT_FN_PDF_LIGHT = 4,     /* in: point3 l3 (6)                        out: 1         distributions.rs:160-184 */
+    RT_FN_PDF_MIX = 5,       /* in: point3 n3 l3 v3 rough (13)           out: 1         distributions.rs:194-201 */
+    RT_FN_SAMPLE_COSINE = 6, /* in: n3 u1 u2 (5)                         out: l3 + sphere3 (6)  :54-63           */
+    RT_FN_SAMPLE_VNDF = 7,   /* in: n3 v3 rough u1 u2 (9)                out: l3        :264-274                 */
+    RT_FN_SAMPLE_LIGHT = 8,  /* in: point3 light_index u v (6)           out: l3        :111-125,151-158         */
+    RT_FN_PHILOX = 9         /* in: pixel sample call seed_lo (4, as exact integers) out: 4 (u32 as float bits)  */
+};
+int rt_eval(RtScene* scene_or_null, int32_t fn, const float* in, int64_t n, float* out);
+
+/* ---- output (main.rs:88-95) ------------------------------------------------------------------------------ */
+/* "P6\n{W} {H}\n255\n" + bytes.  append != 0 reproduces the reference's append-mode open (main.rs:62-66). */
+int rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb, int32_t append);
+
+/* ---- roofline support ------------------------------------------------------------------------------------ */
+/* FFMA issue micro-benchmark on `device`: measured FP32 TFLOP/s (2 flop per FMA lane) and SM clock in MHz. */
+int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_mhz);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_API_H */

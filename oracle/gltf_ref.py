@@ -145,7 +145,12 @@ class _Doc:
             self.j = json.load(f)
         self.buffers = []
         for b in self.j.get("buffers", []):
-            with open(os.path.join(self.dir, b["uri"]), "rb") as f:
+            uri = b["uri"]
+            if uri.startswith("data:"):                      # gltf::import decodes base64 data URIs
+                import base64
+                self.buffers.append(base64.b64decode(uri.split(",", 1)[1]))
+                continue
+            with open(os.path.join(self.dir, uri), "rb") as f:
                 self.buffers.append(f.read())
 
     def accessor(self, idx):
@@ -185,7 +190,8 @@ def convert_gltf_to_scene(path: str, width: int, height: int, samples: int) -> F
         local_m, r = _node_transform(node)
         # Quaternion::new(w, i, j, k) * rotation, then normalised (UnitQuaternion::from_quaternion)  :112-117
         q = _quat_mul(np.array([r[3], r[0], r[1], r[2]], dtype=np.float64), rotation)
-        current_rotation = q / np.sqrt(np.dot(q, q))
+        # Unit::new_normalize: q / sqrt(i^2 + j^2 + k^2 + w^2) (nalgebra stores quaternion coords as [i, j, k, w])
+        current_rotation = q / np.sqrt(q[1] * q[1] + q[2] * q[2] + q[3] * q[3] + q[0] * q[0])
         m = transformation @ local_m                                                    # :127
         if "camera" in node:
             cam = j["cameras"][node["camera"]]

@@ -1,0 +1,191 @@
+// bvh_builder.cpp -- host SAH builder producing the device BVH layout (FlatBvh, host_scene.h).
+//
+// Takes the place of create_bvh_tree / create_bvh_node / try_split (bvh.rs:26-144) for the device path.  Node
+// order and shape are NOT observable through render_scene (only nearest-hit results and box containment are),
+// so this is a different tree on purpose:
+//   * the same objective family -- full-sweep surface-area heuristic over the three axes on EPS-padded triangle
+//     boxes (aabb.rs:53-65), half-area x*y+y*z+z*x like Aabb::area (aabb.rs:32-38) -- but with a traversal-cost
+//     term and leaves that may be split below 4 triangles when that is cheaper for the GPU traversal;
+//   * O(n log^2 n): one sort per axis per level, boxes cached (the reference recomputes them in the comparator);
+//   * output is a pre-order array of child-pair nodes with float boxes rounded outward.
+#include <algorithm>
+#include <cmath>
+#include <cstring>
+#include <limits>
+
+#include "host_scene.h"
+
+namespace rtb {
+namespace {
+
+const double kEps = 0.00001;  // geometry.rs:49
+const double kInf = std::numeric_limits<double>::infinity();
+
+struct Box {
+    double mn[3], mx[3];
+    void reset() { for (int a = 0; a < 3; ++a) { mn[a] = kInf; mx[a] = -kInf; } }
+    void grow(const Box& o) { for (int a = 0; a < 3; ++a) { mn[a] = std::min(mn[a], o.mn[a]); mx[a] = std::max(mx[a], o.mx[a]); } }
+    double half_area() const { double x = mx[0] - mn[0], y = mx[1] - mn[1], z = mx[2] - mn[2]; return x * y + y * z + z * x; }
+};
+
+struct TempNode { Box box; int left = -1, right = -1, first = 0, count = 0; };
+
+Box tri_box(const double* v) {  // aabb.rs:53-65: min/max of the vertices -/+ EPS
+    Box b;
+    for (int a = 0; a < 3; ++a) {
+        b.mn[a] = std::min(std::min(v[a], v[3 + a]), v[6 + a]) - kEps;
+        b.mx[a] = std::max(std::max(v[a], v[3 + a]), v[6 + a]) + kEps;
+    }
+    return b;
+}
+
+float round_down(double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity()); return f; }
+float round_up(double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity()); return f; }
+
+struct Build {
+    const double* tri_v;
+    const BvhBuildParams& p;
+    std::vector<Box> boxes;        // per original triangle id (only those in `order` are valid)
+    std::vector<int32_t> order;    // being permuted
+    std::vector<TempNode> nodes;
+    std::vector<double> right_area;
+
+    int build(int first, int count, int depth, int* max_depth) {
+        TempNode n;
+        n.box.reset();
+        for (int i = first; i < first + count; ++i) n.box.grow(boxes[(size_t)order[(size_t)i]]);
+        n.first = first; n.count = count;
+        *max_depth = std::max(*max_depth, depth);
+        int self = (int)nodes.size();
+        nodes.push_back(n);
+        if (count <= 1) return self;
+
+        double best_cost = kInf; int best_axis = -1, best_split = -1;
+        right_area.resize((size_t)count);
+        for (int axis = 0; axis < 3; ++axis) {
+            sort_axis(first, count, axis);
+            Box acc; acc.reset();
+            for (int i = count - 1; i > 0; --i) { acc.grow(boxes[(size_t)order[(size_t)(first + i)]]); right_area[(size_t)i] = acc.half_area(); }
+            acc.reset();
+            for (int i = 0; i + 1 < count; ++i) {
+                acc.grow(boxes[(size_t)order[(size_t)(first + i)]]);
+                double cost = (double)(i + 1) * acc.half_area() + (double)(count - i - 1) * right_area[(size_t)(i + 1)];
+                if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i + 1; }
+            }
+        }
+        double parent_area = n.box.half_area();
+        double split_cost = p.traversal_cost * parent_area + best_cost;
+        double leaf_cost = (double)count * parent_area;
+        bool can_leaf = count <= p.max_leaf_size && count <= 8;
+        if (can_leaf && leaf_cost <= split_cost) return self;
+        if (best_axis < 0 || !(best_cost < kInf)) {  // degenerate boxes (NaN/inf input): median split on x
+            best_axis = 0; best_split = count / 2;
+        }
+        sort_axis(first, count, best_axis);
+        int l = build(first, best_split, depth + 1, max_depth);
+        int r = build(first + best_split, count - best_split, depth + 1, max_depth);
+        nodes[(size_t)self].left = l; nodes[(size_t)self].right = r;
+        return self;
+    }
+
+    void sort_axis(int first, int count, int axis) {
+        std::sort(order.begin() + first, order.begin() + first + count, [this, axis](int32_t x, int32_t y) {
+            double cx = boxes[(size_t)x].mn[axis] + boxes[(size_t)x].mx[axis], cy = boxes[(size_t)y].mn[axis] + boxes[(size_t)y].mx[axis];
+            if (cx != cy) return cx < cy;
+            return x < y;  // deterministic order for equal centres
+        });
+    }
+};
+
+void put_box(FlatBvh* out, int node, int slot, const Box& b) {
+    float* A = &out->box_a[(size_t)node * 4]; float* B = &out->box_b[(size_t)node * 4]; float* C = &out->box_c[(size_t)node * 4];
+    float* xy = slot == 0 ? A : B;
+    xy[0] = round_down(b.mn[0]); xy[1] = round_up(b.mx[0]); xy[2] = round_down(b.mn[1]); xy[3] = round_up(b.mx[1]);
+    C[slot * 2 + 0] = round_down(b.mn[2]); C[slot * 2 + 1] = round_up(b.mx[2]);
+}
+
+int32_t leaf_ref(int first, int count) { return ~(int32_t)(((uint32_t)first << 3) | (uint32_t)(count - 1)); }
+
+int emit(const Build& b, int t, FlatBvh* out) {
+    int self = out->n_nodes++;
+    out->box_a.resize((size_t)out->n_nodes * 4); out->box_b.resize((size_t)out->n_nodes * 4); out->box_c.resize((size_t)out->n_nodes * 4);
+    out->child.resize((size_t)out->n_nodes * 2);
+    int kids[2] = {b.nodes[(size_t)t].left, b.nodes[(size_t)t].right};
+    for (int s = 0; s < 2; ++s) {
+        const TempNode& c = b.nodes[(size_t)kids[s]];
+        put_box(out, self, s, c.box);
+        int32_t ref;
+        if (c.left < 0) { ref = leaf_ref(c.first, c.count); out->n_leaves++; out->max_leaf = std::max(out->max_leaf, c.count); }
+        else ref = emit(b, kids[s], out);
+        out->child[(size_t)self * 2 + (size_t)s] = ref;
+    }
+    return self;
+}
+
+}  // namespace
+
+void build_bvh(const double* tri_v, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out) {
+    *out = FlatBvh();
+    Build b{tri_v, p, {}, ids, {}, {}};
+    int32_t max_id = -1;
+    for (int32_t id : ids) max_id = std::max(max_id, id);
+    b.boxes.resize((size_t)(max_id + 1));
+    for (int32_t id : ids) b.boxes[(size_t)id] = tri_box(tri_v + (size_t)id * 9);
+    int max_depth = 0;
+    if (!ids.empty()) b.build(0, (int)ids.size(), 1, &max_depth);
+    out->tri_order = b.order;
+    out->depth = max_depth;
+    if (!ids.empty() && b.nodes[0].left >= 0) {
+        emit(b, 0, out);
+        return;
+    }
+    // Root is a leaf (or the set is empty): wrap it in one pair node whose second child is a far-away point box
+    // that no practical ray reaches (its leaf re-tests triangle 0, which cannot change the nearest hit).
+    out->n_nodes = 1;
+    out->box_a.assign(4, 0.f); out->box_b.assign(4, 0.f); out->box_c.assign(4, 0.f); out->child.assign(2, 0);
+    Box far; for (int a = 0; a < 3; ++a) { far.mn[a] = 1e30; far.mx[a] = 1e30; }
+    if (ids.empty()) {
+        put_box(out, 0, 0, far); put_box(out, 0, 1, far);
+        out->child[0] = leaf_ref(0, 1); out->child[1] = leaf_ref(0, 1);   // caller supplies one degenerate triangle
+        out->n_leaves = 0; out->max_leaf = 0; out->depth = 1;
+    } else {
+        put_box(out, 0, 0, b.nodes[0].box); put_box(out, 0, 1, far);
+        out->child[0] = leaf_ref(0, (int)ids.size()); out->child[1] = leaf_ref(0, 1);
+        out->n_leaves = 1; out->max_leaf = (int)ids.size(); out->depth = 2;
+    }
+}
+
+int validate_flat_bvh(const FlatBvh& bvh, const double* tri_v) {
+    int bad = 0;
+    auto slot_box = [&bvh](int node, int s, float mn[3], float mx[3]) {
+        const float* A = &bvh.box_a[(size_t)node * 4]; const float* B = &bvh.box_b[(size_t)node * 4]; const float* C = &bvh.box_c[(size_t)node * 4];
+        const float* xy = s == 0 ? A : B;
+        mn[0] = xy[0]; mx[0] = xy[1]; mn[1] = xy[2]; mx[1] = xy[3]; mn[2] = C[s * 2]; mx[2] = C[s * 2 + 1];
+    };
+    for (int n = 0; n < bvh.n_nodes; ++n) {
+        for (int s = 0; s < 2; ++s) {
+            float mn[3], mx[3];
+            slot_box(n, s, mn, mx);
+            int32_t ref = bvh.child[(size_t)n * 2 + (size_t)s];
+            if (mn[0] > 1e29f) continue;  // the far-away filler box
+            if (ref < 0) {
+                uint32_t code = (uint32_t)~ref; int first = (int)(code >> 3), count = (int)(code & 7u) + 1;
+                if (bvh.tri_order.empty()) continue;
+                for (int i = first; i < first + count; ++i) {
+                    Box tb = tri_box(tri_v + (size_t)bvh.tri_order[(size_t)i] * 9);
+                    for (int a = 0; a < 3; ++a) if (!((double)mn[a] <= tb.mn[a] && (double)mx[a] >= tb.mx[a])) { ++bad; break; }
+                }
+            } else {
+                for (int cs = 0; cs < 2; ++cs) {
+                    float cmn[3], cmx[3];
+                    slot_box(ref, cs, cmn, cmx);
+                    if (cmn[0] > 1e29f) continue;
+                    for (int a = 0; a < 3; ++a) if (!(mn[a] <= cmn[a] && mx[a] >= cmx[a])) { ++bad; break; }
+                }
+            }
+        }
+    }
+    return bad;
+}
+
+}  // namespace rtb

@@ -1,0 +1,54 @@
+// host_scene.h -- host-side scene types shared by the loader, the BVH builder and the C ABI.
+#pragma once
+#include <cstdint>
+#include <string>
+#include <vector>
+
+namespace rtb {
+
+// The reference's `Scene` (src/scene.rs:22-39) flattened, f64 like the reference (geometry.rs:5), load order.
+struct HostScene {
+    int32_t width = 0, height = 0, samples = 0, ray_depth = 6;
+    double bg_color[3] = {0, 0, 0};
+    double camera_position[3] = {0, 0, 0}, camera_forward[3] = {0, 0, 0}, camera_right[3] = {0, 0, 0}, camera_up[3] = {0, 0, 0};
+    double camera_fov_x = 0, camera_fov_y = 0;
+    std::vector<double> tri_v;         // n x 9
+    std::vector<double> tri_n;         // n x 9
+    std::vector<double> tri_material;  // n x 5  (base rgb, metallic, roughness)
+    std::vector<double> tri_emission;  // n x 3
+    int32_t n_tris() const { return (int32_t)(tri_v.size() / 9); }
+};
+
+// Loader status: ok, or a message + an RT_ERR_* class.
+struct LoadError { int code = 0; std::string message; };
+
+// main.rs:45-47: gltf::import(path) + convert_gltf_to_scene(..., width, height, samples).
+bool load_gltf_scene(const std::string& path, int32_t width, int32_t height, int32_t samples, HostScene* out, LoadError* err);
+
+// ---- flattened device-layout BVH (built on the host, bvh_builder.cpp) ---------------------------------------
+// Binary BVH stored as "child-pair" nodes: inner node i keeps the boxes of BOTH children, so one visit tests two
+// boxes and descends without fetching the children's own nodes.  A child reference is >= 0 for an inner node
+// index and < 0 for a leaf: ~((first_tri << 3) | (count - 1)), first_tri indexing the BVH-ordered triangle
+// arrays, count in 1..8.  Node 0 is the root.  Boxes are the reference's EPS-padded triangle bounds
+// (aabb.rs:53-65) rounded OUTWARD to float, so the device slab test is conservative w.r.t. the f64 boxes.
+struct FlatBvh {
+    std::vector<float> box_a;     // n_nodes x 4: c0.min.x, c0.max.x, c0.min.y, c0.max.y
+    std::vector<float> box_b;     // n_nodes x 4: c1.min.x, c1.max.x, c1.min.y, c1.max.y
+    std::vector<float> box_c;     // n_nodes x 4: c0.min.z, c0.max.z, c1.min.z, c1.max.z
+    std::vector<int32_t> child;   // n_nodes x 2
+    std::vector<int32_t> tri_order;  // BVH order -> original triangle id
+    int32_t n_nodes = 0, n_leaves = 0, depth = 0, max_leaf = 0;
+};
+
+struct BvhBuildParams {
+    int max_leaf_size = 4;       // bvh.rs:89 (n <= 4 never splits)
+    double traversal_cost = 1.0; // cost of one box test relative to one triangle test in the SAH
+};
+
+// tri_v: n x 9 doubles (load order); ids: which triangles to include (all, or the lights).
+void build_bvh(const double* tri_v, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out);
+// validate_bvh (bvh.rs:299-322) on the flattened tree: every leaf box contains its triangles' EPS-padded
+// boxes, every inner pair box contains the boxes stored in the child node.  Returns the number of violations.
+int validate_flat_bvh(const FlatBvh& bvh, const double* tri_v);
+
+}  // namespace rtb

@@ -1,0 +1,70 @@
+// main.cpp -- the `raytracing-engine` CLI with the reference's argv (src/main.rs:28-73, run.sh:2):
+//     raytracing-engine <scene.gltf> <width> <height> <samples> <out.ppm> [png_basename]
+// Scene ingest, rendering and output all go through the C ABI (include/rt_api.h); this file is what main.rs
+// becomes once render_scene is the B200 library.  Differences from the reference, on purpose:
+//   * errors are reported and the exit code is non-zero (the reference panics);
+//   * the PPM is truncated, not appended to (main.rs:62-66 opens with append(true), which stacks a second image
+//     behind an existing file); set RT_PPM_APPEND=1 to get the reference behaviour;
+//   * the optional 6th argument (PNG dump, main.rs:68-72) is accepted; no PNG encoder is linked in this build,
+//     so it writes `<basename>.ppm` next to it instead and says so.
+// Extra knobs are environment variables only, so the positional CLI stays drop-in:
+//   RT_SEED (Philox key, default 0), RT_DEVICE (CUDA device, default 0), RT_STATS=1 (work counters).
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_api.h"
+
+static long long env_ll(const char* name, long long dflt) { const char* v = std::getenv(name); return v && *v ? std::atoll(v) : dflt; }
+
+int main(int argc, char** argv) {
+    if (argc < 6) {
+        std::fprintf(stderr, "usage: %s <scene.gltf> <width> <height> <samples> <out.ppm> [png_basename]\n", argv[0]);
+        return 2;
+    }
+    const char* input_scene = argv[1];
+    const int width = std::atoi(argv[2]), height = std::atoi(argv[3]), samples = std::atoi(argv[4]);
+    const char* output_ppm = argv[5];
+    const int device = (int)env_ll("RT_DEVICE", 0);
+
+    RtScene* scene = nullptr;
+    if (rt_scene_load_gltf(input_scene, width, height, samples, device, &scene) != RT_OK) {
+        std::fprintf(stderr, "error: %s\n", rt_last_error());
+        return 1;
+    }
+    RtSceneInfo info;
+    rt_scene_info(scene, &info);
+    std::printf("Scene finite primitives: %d, light sources: %d\n", info.n_tris, info.n_lights);   // main.rs:49-53
+
+    std::vector<uint8_t> rendered((size_t)width * (size_t)height * 3);
+    RtRenderParams params = {};
+    params.seed = (uint64_t)env_ll("RT_SEED", 0);
+    params.collect_stats = (int)env_ll("RT_STATS", 0);
+    RtStats stats;
+    const auto start = std::chrono::steady_clock::now();                                           // main.rs:54
+    if (rt_render(scene, &params, rendered.data(), &stats) != RT_OK) {
+        std::fprintf(stderr, "error: %s\n", rt_last_error());
+        rt_scene_destroy(scene);
+        return 1;
+    }
+    const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
+    std::printf("Rendering took %.6fs\n", secs);                                                   // main.rs:57-58
+    const double msamples = (double)width * height * samples / secs / 1e6;
+    std::printf("{\"msamples_per_s\": %.3f, \"kernel_ms\": %.3f, \"total_ms\": %.3f, \"segments\": %llu}\n", msamples, stats.kernel_ms, stats.total_ms,
+                (unsigned long long)stats.segments);
+    std::printf("Dumping to %s\n", output_ppm);                                                    // main.rs:59
+    if (rt_write_ppm(output_ppm, width, height, rendered.data(), (int)env_ll("RT_PPM_APPEND", 0)) != RT_OK) {
+        std::fprintf(stderr, "error: %s\n", rt_last_error());
+        rt_scene_destroy(scene);
+        return 1;
+    }
+    if (argc > 6) {
+        const std::string alt = std::string(argv[6]) + ".ppm";
+        std::printf("PNG output is not built in; image dumped to %s instead of %s.png\n", alt.c_str(), argv[6]);
+        rt_write_ppm(alt.c_str(), width, height, rendered.data(), 0);
+    }
+    rt_scene_destroy(scene);
+    return 0;
+}

@@ -1,0 +1,630 @@
+// rt_api.cu -- implementation of the C ABI declared in include/rt_api.h: scene ingest (flatten + BVH build +
+// upload), the render entry points that replace render_scene (rendering.rs:21-69), the nearest-hit query and the
+// test/roofline helpers.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/rt_api.h"
+#include "host_scene.h"
+#include "rt_kernels.h"
+
+namespace {
+
+thread_local std::string g_last_error;
+int fail(int code, const std::string& msg) { g_last_error = msg; return code; }
+#define CUDA_TRY(expr)                                                                                              \
+    do {                                                                                                            \
+        cudaError_t _e = (expr);                                                                                    \
+        if (_e != cudaSuccess) return fail(RT_ERR_CUDA, std::string(#expr) + ": " + cudaGetErrorString(_e));        \
+    } while (0)
+
+const double kEps = 0.00001;  // geometry.rs:49
+
+}  // namespace
+
+struct RtScene {
+    rtb::HostScene host;
+    rtb::FlatBvh bvh, light_bvh;
+    std::vector<int32_t> light_ids;        // load order ids of emissive triangles (gltf_to_scene.rs:240)
+    std::vector<int32_t> light_order;      // device order of the lights -> original id
+    rtd::SceneLayout L;
+    std::vector<char> blob_host;
+    std::vector<double> tri_d_host;        // BVH-ordered a, e1, e2 in f64 (precision-64 queries)
+    int device = 0, sms = 0;
+    int n_mats = 0, validate_failures = 0;
+    uint32_t stack_entries = 16;
+    bool use_smem = false;
+    // device state
+    char* blob_dev = nullptr;
+    double* tri_d_dev = nullptr;
+    float4* layers = nullptr; size_t layers_cap = 0;
+    float4* accum = nullptr; size_t accum_cap = 0;
+    uint8_t* rgb_dev = nullptr; size_t rgb_cap = 0;
+    float* lin_dev = nullptr; size_t lin_cap = 0;
+    unsigned int* work_counter = nullptr;
+    unsigned long long* stats_dev = nullptr;
+    cudaStream_t stream = nullptr;
+    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+};
+
+namespace {
+
+struct BlobWriter {
+    std::vector<char>& buf;
+    uint32_t add(const void* data, size_t bytes) {
+        size_t off = (buf.size() + 15u) & ~(size_t)15u;
+        buf.resize(off + ((bytes + 15u) & ~(size_t)15u), 0);
+        if (bytes) std::memcpy(buf.data() + off, data, bytes);
+        return (uint32_t)off;
+    }
+};
+
+inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
+
+int env_int(const char* name, int dflt) { const char* v = std::getenv(name); return v && *v ? std::atoi(v) : dflt; }
+double env_double(const char* name, double dflt) { const char* v = std::getenv(name); return v && *v ? std::atof(v) : dflt; }
+
+// Flatten the host scene into the device blob (rt_device.cuh SceneLayout).
+int flatten_scene(RtScene* s) {
+    const rtb::HostScene& h = s->host;
+    const int n = h.n_tris();
+    rtb::BvhBuildParams bp;
+    bp.max_leaf_size = env_int("RT_BVH_MAX_LEAF", 4);
+    bp.traversal_cost = env_double("RT_BVH_TRAV_COST", 1.0);
+    if (bp.max_leaf_size < 1) bp.max_leaf_size = 1;
+    if (bp.max_leaf_size > 8) bp.max_leaf_size = 8;
+    std::vector<int32_t> all((size_t)n);
+    for (int i = 0; i < n; ++i) all[(size_t)i] = i;
+    rtb::build_bvh(h.tri_v.data(), all, bp, &s->bvh);
+    s->validate_failures = rtb::validate_flat_bvh(s->bvh, h.tri_v.data());
+
+    // lights: emission.norm() > EPS (gltf_to_scene.rs:240)
+    s->light_ids.clear();
+    for (int i = 0; i < n; ++i) {
+        const double* e = &h.tri_emission[(size_t)i * 3];
+        if (std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) > kEps) s->light_ids.push_back(i);
+    }
+    const int n_lights = (int)s->light_ids.size();
+    const bool use_light_bvh = n_lights > RT_BRUTE_LIGHTS;
+    if (use_light_bvh) {
+        rtb::build_bvh(h.tri_v.data(), s->light_ids, bp, &s->light_bvh);
+        s->validate_failures += rtb::validate_flat_bvh(s->light_bvh, h.tri_v.data());
+        s->light_order = s->light_bvh.tri_order;
+    } else {
+        s->light_bvh = rtb::FlatBvh();
+        s->light_order = s->light_ids;
+    }
+
+    // materials: per-primitive in the reference (scene.rs:13-20); deduplicated by value for the device table
+    std::map<std::vector<double>, int> mat_index;
+    std::vector<float> mat0, mat1;
+    std::vector<int32_t> tri_mat((size_t)n);
+    for (int i = 0; i < n; ++i) {
+        std::vector<double> key(8);
+        for (int k = 0; k < 5; ++k) key[(size_t)k] = h.tri_material[(size_t)i * 5 + (size_t)k];
+        for (int k = 0; k < 3; ++k) key[(size_t)(5 + k)] = h.tri_emission[(size_t)i * 3 + (size_t)k];
+        auto it = mat_index.find(key);
+        if (it == mat_index.end()) {
+            int id = (int)mat_index.size();
+            mat_index[key] = id;
+            mat0.insert(mat0.end(), {(float)key[0], (float)key[1], (float)key[2], (float)key[3]});
+            mat1.insert(mat1.end(), {(float)key[5], (float)key[6], (float)key[7], (float)key[4]});
+            tri_mat[(size_t)i] = id;
+        } else tri_mat[(size_t)i] = it->second;
+    }
+    if (mat0.empty()) { mat0.assign(4, 0.f); mat1.assign(4, 0.f); }
+    s->n_mats = (int)mat_index.size();
+
+    // BVH-ordered triangle + shading arrays
+    const int nt = n > 0 ? n : 1;   // an empty scene keeps one degenerate triangle (never hit: det == 0)
+    std::vector<float> tri_a((size_t)nt * 4, 0.f), tri_e1((size_t)nt * 4, 0.f), tri_e2((size_t)nt * 4, 0.f);
+    std::vector<float> sh_n0((size_t)nt * 4, 0.f), sh_dn1((size_t)nt * 4, 0.f), sh_dn2((size_t)nt * 4, 0.f), sh_ng((size_t)nt * 4, 0.f);
+    s->tri_d_host.assign((size_t)nt * 9, 0.0);
+    sh_dn1[3] = i2f(-1);
+    for (int k = 0; k < n; ++k) {
+        const int id = s->bvh.tri_order[(size_t)k];
+        const double* v = &h.tri_v[(size_t)id * 9];
+        const double* nn = &h.tri_n[(size_t)id * 9];
+        double e1[3], e2[3];
+        for (int a = 0; a < 3; ++a) { e1[a] = v[3 + a] - v[a]; e2[a] = v[6 + a] - v[a]; }
+        double ng[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        const double len = std::sqrt(ng[0] * ng[0] + ng[1] * ng[1] + ng[2] * ng[2]);
+        for (int a = 0; a < 3; ++a) {
+            tri_a[(size_t)k * 4 + (size_t)a] = (float)v[a];
+            tri_e1[(size_t)k * 4 + (size_t)a] = (float)e1[a];
+            tri_e2[(size_t)k * 4 + (size_t)a] = (float)e2[a];
+            sh_n0[(size_t)k * 4 + (size_t)a] = (float)nn[a];
+            sh_dn1[(size_t)k * 4 + (size_t)a] = (float)(nn[3 + a] - nn[a]);
+            sh_dn2[(size_t)k * 4 + (size_t)a] = (float)(nn[6 + a] - nn[a]);
+            sh_ng[(size_t)k * 4 + (size_t)a] = (float)(ng[a] / len);
+            s->tri_d_host[(size_t)k * 9 + (size_t)a] = v[a];
+            s->tri_d_host[(size_t)k * 9 + 3 + (size_t)a] = e1[a];
+            s->tri_d_host[(size_t)k * 9 + 6 + (size_t)a] = e2[a];
+        }
+        sh_n0[(size_t)k * 4 + 3] = i2f(tri_mat[(size_t)id]);
+        sh_dn1[(size_t)k * 4 + 3] = i2f(id);
+    }
+    // light arrays (device light order)
+    const int nl = n_lights > 0 ? n_lights : 1;
+    std::vector<float> lt_a((size_t)nl * 4, 0.f), lt_e1((size_t)nl * 4, 0.f), lt_e2((size_t)nl * 4, 0.f), lt_ng((size_t)nl * 4, 0.f);
+    for (int k = 0; k < n_lights; ++k) {
+        const int id = s->light_order[(size_t)k];
+        const double* v = &h.tri_v[(size_t)id * 9];
+        double e1[3], e2[3];
+        for (int a = 0; a < 3; ++a) { e1[a] = v[3 + a] - v[a]; e2[a] = v[6 + a] - v[a]; }
+        double ng[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        const double len = std::sqrt(ng[0] * ng[0] + ng[1] * ng[1] + ng[2] * ng[2]);
+        for (int a = 0; a < 3; ++a) {
+            lt_a[(size_t)k * 4 + (size_t)a] = (float)v[a];
+            lt_e1[(size_t)k * 4 + (size_t)a] = (float)e1[a];
+            lt_e2[(size_t)k * 4 + (size_t)a] = (float)e2[a];
+            lt_ng[(size_t)k * 4 + (size_t)a] = (float)(ng[a] / len);
+        }
+        lt_a[(size_t)k * 4 + 3] = (float)(1.0 / (len * 0.5));     // get_local_pdf distributions.rs:76-79
+    }
+
+    s->blob_host.clear();
+    BlobWriter w{s->blob_host};
+    rtd::SceneLayout& L = s->L;
+    std::memset(&L, 0, sizeof(L));
+    L.box_a = w.add(s->bvh.box_a.data(), s->bvh.box_a.size() * 4);
+    L.box_b = w.add(s->bvh.box_b.data(), s->bvh.box_b.size() * 4);
+    L.box_c = w.add(s->bvh.box_c.data(), s->bvh.box_c.size() * 4);
+    L.child = w.add(s->bvh.child.data(), s->bvh.child.size() * 4);
+    L.tri_a = w.add(tri_a.data(), tri_a.size() * 4);
+    L.tri_e1 = w.add(tri_e1.data(), tri_e1.size() * 4);
+    L.tri_e2 = w.add(tri_e2.data(), tri_e2.size() * 4);
+    L.sh_n0 = w.add(sh_n0.data(), sh_n0.size() * 4);
+    L.sh_dn1 = w.add(sh_dn1.data(), sh_dn1.size() * 4);
+    L.sh_dn2 = w.add(sh_dn2.data(), sh_dn2.size() * 4);
+    L.sh_ng = w.add(sh_ng.data(), sh_ng.size() * 4);
+    L.mat0 = w.add(mat0.data(), mat0.size() * 4);
+    L.mat1 = w.add(mat1.data(), mat1.size() * 4);
+    L.lt_a = w.add(lt_a.data(), lt_a.size() * 4);
+    L.lt_e1 = w.add(lt_e1.data(), lt_e1.size() * 4);
+    L.lt_e2 = w.add(lt_e2.data(), lt_e2.size() * 4);
+    L.lt_ng = w.add(lt_ng.data(), lt_ng.size() * 4);
+    if (use_light_bvh) {
+        L.lbox_a = w.add(s->light_bvh.box_a.data(), s->light_bvh.box_a.size() * 4);
+        L.lbox_b = w.add(s->light_bvh.box_b.data(), s->light_bvh.box_b.size() * 4);
+        L.lbox_c = w.add(s->light_bvh.box_c.data(), s->light_bvh.box_c.size() * 4);
+        L.lchild = w.add(s->light_bvh.child.data(), s->light_bvh.child.size() * 4);
+    }
+    L.total_bytes = (uint32_t)s->blob_host.size();
+    L.n_nodes = s->bvh.n_nodes; L.n_tris = n; L.n_mats = s->n_mats; L.n_lights = n_lights;
+    L.n_lnodes = s->light_bvh.n_nodes; L.light_bvh = use_light_bvh ? 1 : 0;
+
+    const int need = std::max(s->bvh.depth, s->light_bvh.depth) + 2;
+    if (need <= 16) s->stack_entries = 16;
+    else if (need <= 32) s->stack_entries = 32;
+    else if (need <= 64) s->stack_entries = 64;
+    else return fail(RT_ERR_LIMIT, "BVH depth " + std::to_string(need - 2) + " exceeds the 62-entry traversal stack");
+    const int smem_limit = env_int("RT_SMEM_SCENE_MAX_BYTES", 48 * 1024);
+    s->use_smem = (int)L.total_bytes <= smem_limit;
+    return RT_OK;
+}
+
+void fill_camera(const rtb::HostScene& h, rtd::Camera* c) {
+    for (int a = 0; a < 3; ++a) {
+        c->pos[a] = (float)h.camera_position[a]; c->right[a] = (float)h.camera_right[a];
+        c->up[a] = (float)h.camera_up[a]; c->fwd[a] = (float)h.camera_forward[a];
+    }
+    c->tan_x = (float)std::tan(h.camera_fov_x * 0.5);     // rendering.rs:76
+    c->tan_y = (float)std::tan(h.camera_fov_y * 0.5);     // rendering.rs:77
+}
+
+int upload_scene(RtScene* s) {
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count <= 0) return fail(RT_ERR_CUDA, std::string("no CUDA device available (there is no CPU fallback): ") + cudaGetErrorString(e));
+    if (s->device < 0 || s->device >= count) return fail(RT_ERR_INVALID, "device index out of range");
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, s->device));
+    CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
+    CUDA_TRY(cudaMalloc((void**)&s->blob_dev, s->blob_host.size()));
+    CUDA_TRY(cudaMemcpy(s->blob_dev, s->blob_host.data(), s->blob_host.size(), cudaMemcpyHostToDevice));
+    CUDA_TRY(cudaMalloc((void**)&s->work_counter, sizeof(unsigned int)));
+    CUDA_TRY(cudaMalloc((void**)&s->stats_dev, sizeof(unsigned long long) * rtd::RT_N_STATS));
+    return RT_OK;
+}
+
+int finish_create(RtScene* s, RtScene** out) {
+    int rc = flatten_scene(s);
+    if (rc == RT_OK && s->device >= 0) rc = upload_scene(s);   // device < 0: host-only scene (loader / BVH inspection)
+    if (rc != RT_OK) { rt_scene_destroy(s); return rc; }
+    *out = s;
+    return RT_OK;
+}
+
+template <class T>
+int ensure(T** p, size_t* cap, size_t need_elems) {
+    if (*cap >= need_elems && *p) return RT_OK;
+    if (*p) cudaFree(*p);
+    *p = nullptr; *cap = 0;
+    cudaError_t e = cudaMalloc((void**)p, need_elems * sizeof(T));
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
+    *cap = need_elems;
+    return RT_OK;
+}
+
+struct RenderPlan { rtd::RenderArgs args; bool use_smem; bool stats; };
+
+// Shared front half of the three render entry points: launches the path-tracing kernel into s->layers.
+int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, RenderPlan* plan, rtd::KernelInfo* ki) {
+    const rtb::HostScene& h = s->host;
+    if (!s->blob_dev) return fail(RT_ERR_CUDA, "scene is host-only (created with device < 0): rendering needs a CUDA device, there is no CPU fallback");
+    if (h.width <= 0 || h.height <= 0) return fail(RT_ERR_INVALID, "width and height must be positive");
+    if (h.samples <= 0) return fail(RT_ERR_INVALID, "samples must be positive (the reference panics on an empty reduce, rendering.rs:60)");
+    RtRenderParams dflt;
+    std::memset(&dflt, 0, sizeof(dflt));
+    if (!p) p = &dflt;
+    int s0 = p->sample_begin, s1 = p->sample_end;
+    if (s0 == 0 && s1 == 0) s1 = h.samples;
+    if (s0 < 0 || s1 > h.samples || s0 >= s1) return fail(RT_ERR_INVALID, "sample range must satisfy 0 <= begin < end <= samples");
+    if ((uint64_t)h.width * (uint64_t)h.height > (1ull << 30)) return fail(RT_ERR_LIMIT, "frame larger than 2^30 pixels");
+    CUDA_TRY(cudaSetDevice(s->device));
+
+    rtd::RenderArgs& a = plan->args;
+    std::memset(&a, 0, sizeof(a));
+    a.blob = s->blob_dev; a.L = s->L;
+    fill_camera(h, &a.cam);
+    for (int k = 0; k < 3; ++k) a.bg[k] = (float)h.bg_color[k];
+    a.W = h.width; a.H = h.height; a.ray_depth = h.ray_depth;
+    a.max_attempts = p->max_attempts > 0 ? p->max_attempts : 64;
+    a.n_comp = s->L.n_lights > 0 ? 3 : 2;                     // rendering.rs:23-31
+    a.s_begin = s0; a.s_end = s1;
+    a.tiles_x = (uint32_t)((h.width + 7) / 8);
+    const uint32_t tiles_y = (uint32_t)((h.height + 3) / 4);
+    a.n_pix_items = a.tiles_x * tiles_y * 32u;
+    a.stack_entries = s->stack_entries;
+    a.seed_lo = (uint32_t)(p->seed & 0xffffffffu); a.seed_hi = (uint32_t)(p->seed >> 32);
+    plan->stats = p->collect_stats != 0;
+    plan->use_smem = s->use_smem;
+    if (p->kernel_variant == 1) plan->use_smem = false;
+    if (p->kernel_variant == 2) plan->use_smem = true;
+
+    // sample chunks: enough (pixel, chunk) items to keep every resident lane busy ~4 times over
+    int lanes = 0;
+    CUDA_TRY(rtd::render_resident_lanes(plan->use_smem, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
+    const int n_samp = s1 - s0;
+    long long want = (4LL * lanes + a.n_pix_items - 1) / a.n_pix_items;
+    if (want < 1) want = 1;
+    if (want > n_samp) want = n_samp;
+    const size_t n_pix = (size_t)h.width * (size_t)h.height;
+    const long long max_layers = std::max<long long>(1, (long long)((1ull << 30) / (n_pix * sizeof(float4))));
+    if (want > max_layers) want = max_layers;
+    a.chunk_size = (int)((n_samp + want - 1) / want);
+    a.n_chunks = (n_samp + a.chunk_size - 1) / a.chunk_size;
+    const uint64_t total = (uint64_t)a.n_pix_items * (uint64_t)a.n_chunks;
+    if (total >= 0xffffffffull) return fail(RT_ERR_LIMIT, "too many work items");
+    a.total_items = (uint32_t)total;
+
+    int rc = ensure(&s->layers, &s->layers_cap, n_pix * (size_t)a.n_chunks);
+    if (rc != RT_OK) return rc;
+    a.layers = s->layers; a.work_counter = s->work_counter; a.stats = s->stats_dev;
+    CUDA_TRY(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
+    if (plan->stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, sizeof(unsigned long long) * rtd::RT_N_STATS, stream));
+    CUDA_TRY(rtd::launch_render(a, plan->use_smem, plan->stats, s->sms, stream, ki));
+    return RT_OK;
+}
+
+int collect_stats(RtScene* s, const RenderPlan& plan, RtStats* st, int launches, cudaStream_t stream) {
+    if (!st) return RT_OK;
+    std::memset(st, 0, sizeof(*st));
+    st->kernel_launches = (uint64_t)launches;
+    if (plan.stats) {
+        unsigned long long v[rtd::RT_N_STATS];
+        CUDA_TRY(cudaMemcpyAsync(v, s->stats_dev, sizeof(v), cudaMemcpyDeviceToHost, stream));
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        st->samples = v[rtd::RT_STAT_SAMPLES]; st->segments = v[rtd::RT_STAT_SEGMENTS]; st->vertices = v[rtd::RT_STAT_VERTICES];
+        st->attempts = v[rtd::RT_STAT_ATTEMPTS]; st->node_tests = v[rtd::RT_STAT_NODE_TESTS]; st->tri_tests = v[rtd::RT_STAT_TRI_TESTS];
+        st->light_tri_tests = v[rtd::RT_STAT_LIGHT_TRI_TESTS]; st->attempt_cap_hits = v[rtd::RT_STAT_CAP_HITS]; st->nonfinite_samples = v[rtd::RT_STAT_NONFINITE];
+    } else {
+        st->samples = (uint64_t)s->host.width * (uint64_t)s->host.height * (uint64_t)(plan.args.s_end - plan.args.s_begin);
+    }
+    return RT_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* rt_last_error(void) { return g_last_error.c_str(); }
+int rt_api_version(void) { return RT_API_VERSION; }
+int rt_device_count(int32_t* count) {
+    if (!count) return fail(RT_ERR_INVALID, "count is null");
+    int c = 0;
+    cudaError_t e = cudaGetDeviceCount(&c);
+    if (e != cudaSuccess) { *count = 0; return fail(RT_ERR_CUDA, std::string("cudaGetDeviceCount: ") + cudaGetErrorString(e)); }
+    *count = c;
+    return RT_OK;
+}
+
+int rt_scene_load_gltf(const char* path, int32_t width, int32_t height, int32_t samples, int32_t device, RtScene** out) {
+    if (!path || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    RtScene* s = new RtScene();
+    s->device = device;
+    rtb::LoadError err;
+    if (!rtb::load_gltf_scene(path, width, height, samples, &s->host, &err)) { delete s; return fail(err.code, err.message); }
+    return finish_create(s, out);
+}
+
+int rt_scene_create(const RtSceneDesc* d, int32_t device, RtScene** out) {
+    if (!d || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    if (d->n_tris < 0) return fail(RT_ERR_INVALID, "n_tris < 0");
+    if (d->n_tris > 0 && (!d->tri_v || !d->tri_n || !d->tri_material || !d->tri_emission)) return fail(RT_ERR_INVALID, "null triangle array");
+    RtScene* s = new RtScene();
+    s->device = device;
+    rtb::HostScene& h = s->host;
+    h.width = d->width; h.height = d->height; h.samples = d->samples; h.ray_depth = d->ray_depth;
+    for (int a = 0; a < 3; ++a) {
+        h.bg_color[a] = d->bg_color[a]; h.camera_position[a] = d->camera_position[a]; h.camera_forward[a] = d->camera_forward[a];
+        h.camera_right[a] = d->camera_right[a]; h.camera_up[a] = d->camera_up[a];
+    }
+    h.camera_fov_x = d->camera_fov_x; h.camera_fov_y = d->camera_fov_y;
+    const size_t n = (size_t)d->n_tris;
+    h.tri_v.assign(d->tri_v, d->tri_v + n * 9); h.tri_n.assign(d->tri_n, d->tri_n + n * 9);
+    h.tri_material.assign(d->tri_material, d->tri_material + n * 5); h.tri_emission.assign(d->tri_emission, d->tri_emission + n * 3);
+    return finish_create(s, out);
+}
+
+void rt_scene_destroy(RtScene* s) {
+    if (!s) return;
+    if (s->stream || s->blob_dev) cudaSetDevice(s->device);
+    cudaFree(s->blob_dev); cudaFree(s->tri_d_dev); cudaFree(s->layers); cudaFree(s->accum); cudaFree(s->rgb_dev); cudaFree(s->lin_dev);
+    cudaFree(s->work_counter); cudaFree(s->stats_dev);
+    for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    if (s->stream) cudaStreamDestroy(s->stream);
+    delete s;
+}
+
+int rt_scene_get_desc(const RtScene* s, RtSceneDesc* d) {
+    if (!s || !d) return fail(RT_ERR_INVALID, "null argument");
+    const rtb::HostScene& h = s->host;
+    std::memset(d, 0, sizeof(*d));
+    d->width = h.width; d->height = h.height; d->samples = h.samples; d->ray_depth = h.ray_depth;
+    for (int a = 0; a < 3; ++a) {
+        d->bg_color[a] = h.bg_color[a]; d->camera_position[a] = h.camera_position[a]; d->camera_forward[a] = h.camera_forward[a];
+        d->camera_right[a] = h.camera_right[a]; d->camera_up[a] = h.camera_up[a];
+    }
+    d->camera_fov_x = h.camera_fov_x; d->camera_fov_y = h.camera_fov_y;
+    d->n_tris = h.n_tris();
+    d->tri_v = h.tri_v.data(); d->tri_n = h.tri_n.data(); d->tri_material = h.tri_material.data(); d->tri_emission = h.tri_emission.data();
+    return RT_OK;
+}
+
+int rt_scene_info(const RtScene* s, RtSceneInfo* o) {
+    if (!s || !o) return fail(RT_ERR_INVALID, "null argument");
+    std::memset(o, 0, sizeof(*o));
+    o->n_tris = s->host.n_tris(); o->n_lights = (int32_t)s->light_ids.size(); o->n_materials = s->n_mats;
+    o->n_nodes = s->bvh.n_nodes; o->n_leaves = s->bvh.n_leaves; o->bvh_depth = s->bvh.depth; o->max_leaf_size = s->bvh.max_leaf;
+    o->bvh_validate_failures = s->validate_failures; o->scene_in_shared_memory = s->use_smem ? 1 : 0; o->device = s->device;
+    o->device_bytes = (int64_t)s->blob_host.size();
+    return RT_OK;
+}
+
+int rt_scene_set_frame(RtScene* s, int32_t width, int32_t height, int32_t samples) {
+    if (!s) return fail(RT_ERR_INVALID, "null scene");
+    s->host.width = width; s->host.height = height; s->host.samples = samples;
+    return RT_OK;
+}
+
+int rt_scene_get_bvh(const RtScene* s, float* nodes, int32_t* tri_order) {
+    if (!s) return fail(RT_ERR_INVALID, "null scene");
+    if (nodes)
+        for (int n = 0; n < s->bvh.n_nodes; ++n) {
+            const float* A = &s->bvh.box_a[(size_t)n * 4]; const float* B = &s->bvh.box_b[(size_t)n * 4]; const float* C = &s->bvh.box_c[(size_t)n * 4];
+            float* o = nodes + (size_t)n * 14;
+            o[0] = A[0]; o[1] = A[2]; o[2] = C[0]; o[3] = A[1]; o[4] = A[3]; o[5] = C[1];
+            o[6] = B[0]; o[7] = B[2]; o[8] = C[2]; o[9] = B[1]; o[10] = B[3]; o[11] = C[3];
+            o[12] = (float)s->bvh.child[(size_t)n * 2]; o[13] = (float)s->bvh.child[(size_t)n * 2 + 1];
+        }
+    if (tri_order) for (size_t k = 0; k < s->bvh.tri_order.size(); ++k) tri_order[k] = s->bvh.tri_order[k];
+    return RT_OK;
+}
+
+// render_scene (rendering.rs:21-69)
+int rt_render(RtScene* s, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st) {
+    if (!s || !rgb_out) return fail(RT_ERR_INVALID, "null argument");
+    if (!s->blob_dev) return fail(RT_ERR_CUDA, "scene is host-only (created with device < 0): rendering needs a CUDA device, there is no CPU fallback");
+    RenderPlan plan; rtd::KernelInfo ki;
+    const size_t n_pix = (size_t)s->host.width * (size_t)s->host.height;
+    cudaStream_t stream = s->stream;
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaEventRecord(s->ev[0], stream));
+    CUDA_TRY(cudaEventRecord(s->ev[1], stream));
+    int rc = render_to_layers(s, p, stream, &plan, &ki);
+    if (rc != RT_OK) return rc;
+    if ((rc = ensure(&s->accum, &s->accum_cap, n_pix)) != RT_OK) return rc;
+    if ((rc = ensure(&s->rgb_dev, &s->rgb_cap, n_pix * 3)) != RT_OK) return rc;
+    CUDA_TRY(rtd::launch_sum_layers(s->layers, plan.args.n_chunks, n_pix, s->accum, false, stream));
+    CUDA_TRY(rtd::launch_resolve_u8(s->accum, n_pix, s->rgb_dev, stream));
+    CUDA_TRY(cudaEventRecord(s->ev[2], stream));
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, s->rgb_dev, n_pix * 3, cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(s->ev[3], stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if ((rc = collect_stats(s, plan, st, 3, stream)) != RT_OK) return rc;
+    if (st) {
+        float k = 0, t = 0;
+        cudaEventElapsedTime(&k, s->ev[1], s->ev[2]); cudaEventElapsedTime(&t, s->ev[0], s->ev[3]);
+        st->kernel_ms = k; st->total_ms = t;
+    }
+    return RT_OK;
+}
+
+int rt_render_linear(RtScene* s, const RtRenderParams* p, float* out, RtStats* st) {
+    if (!s || !out) return fail(RT_ERR_INVALID, "null argument");
+    if (!s->blob_dev) return fail(RT_ERR_CUDA, "scene is host-only (created with device < 0): rendering needs a CUDA device, there is no CPU fallback");
+    RenderPlan plan; rtd::KernelInfo ki;
+    const size_t n_pix = (size_t)s->host.width * (size_t)s->host.height;
+    cudaStream_t stream = s->stream;
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaEventRecord(s->ev[0], stream));
+    int rc = render_to_layers(s, p, stream, &plan, &ki);
+    if (rc != RT_OK) return rc;
+    if ((rc = ensure(&s->accum, &s->accum_cap, n_pix)) != RT_OK) return rc;
+    if ((rc = ensure(&s->lin_dev, &s->lin_cap, n_pix * 3)) != RT_OK) return rc;
+    CUDA_TRY(rtd::launch_sum_layers(s->layers, plan.args.n_chunks, n_pix, s->accum, false, stream));
+    CUDA_TRY(rtd::launch_resolve_linear(s->accum, n_pix, s->lin_dev, stream));
+    CUDA_TRY(cudaEventRecord(s->ev[2], stream));
+    CUDA_TRY(cudaMemcpyAsync(out, s->lin_dev, n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaEventRecord(s->ev[3], stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    if ((rc = collect_stats(s, plan, st, 3, stream)) != RT_OK) return rc;
+    if (st) {
+        float k = 0, t = 0;
+        cudaEventElapsedTime(&k, s->ev[0], s->ev[2]); cudaEventElapsedTime(&t, s->ev[0], s->ev[3]);
+        st->kernel_ms = k; st->total_ms = t;
+    }
+    return RT_OK;
+}
+
+int rt_render_accumulate_device(RtScene* s, const RtRenderParams* p, float* accum_dev, void* stream_v, RtStats* st) {
+    if (!s || !accum_dev) return fail(RT_ERR_INVALID, "null argument");
+    if (!s->blob_dev) return fail(RT_ERR_CUDA, "scene is host-only (created with device < 0): rendering needs a CUDA device, there is no CPU fallback");
+    RenderPlan plan; rtd::KernelInfo ki;
+    const size_t n_pix = (size_t)s->host.width * (size_t)s->host.height;
+    cudaStream_t stream = stream_v ? (cudaStream_t)stream_v : s->stream;
+    CUDA_TRY(cudaSetDevice(s->device));
+    CUDA_TRY(cudaEventRecord(s->ev[0], stream));
+    int rc = render_to_layers(s, p, stream, &plan, &ki);
+    if (rc != RT_OK) return rc;
+    CUDA_TRY(rtd::launch_sum_layers(s->layers, plan.args.n_chunks, n_pix, reinterpret_cast<float4*>(accum_dev), true, stream));
+    CUDA_TRY(cudaEventRecord(s->ev[2], stream));
+    if (st) {
+        CUDA_TRY(cudaStreamSynchronize(stream));
+        if ((rc = collect_stats(s, plan, st, 2, stream)) != RT_OK) return rc;
+        float k = 0;
+        cudaEventElapsedTime(&k, s->ev[0], s->ev[2]);
+        st->kernel_ms = k; st->total_ms = k;
+    }
+    return RT_OK;
+}
+
+int rt_resolve_device(const float* accum_dev, int32_t width, int32_t height, uint8_t* rgb_dev, void* stream_v) {
+    if (!accum_dev || !rgb_dev || width <= 0 || height <= 0) return fail(RT_ERR_INVALID, "bad argument");
+    CUDA_TRY(rtd::launch_resolve_u8(reinterpret_cast<const float4*>(accum_dev), (size_t)width * (size_t)height, rgb_dev, (cudaStream_t)stream_v));
+    return RT_OK;
+}
+
+int rt_trace_primary(RtScene* s, const double* rays, int64_t n, int32_t precision, int32_t* tri_id, double* t) {
+    if (!s || !rays || !tri_id || !t || n < 0) return fail(RT_ERR_INVALID, "bad argument");
+    if (precision != 32 && precision != 64) return fail(RT_ERR_INVALID, "precision must be 32 or 64");
+    if (n == 0) return RT_OK;
+    if (!s->blob_dev) return fail(RT_ERR_CUDA, "scene is host-only: no CUDA device bound, there is no CPU fallback");
+    CUDA_TRY(cudaSetDevice(s->device));
+    if (precision == 64 && !s->tri_d_dev) {
+        CUDA_TRY(cudaMalloc((void**)&s->tri_d_dev, s->tri_d_host.size() * sizeof(double)));
+        CUDA_TRY(cudaMemcpy(s->tri_d_dev, s->tri_d_host.data(), s->tri_d_host.size() * sizeof(double), cudaMemcpyHostToDevice));
+    }
+    double *rays_d = nullptr, *t_d = nullptr; int32_t* id_d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&rays_d, (size_t)n * 6 * sizeof(double)));
+    cudaError_t e = cudaMalloc((void**)&t_d, (size_t)n * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&id_d, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rays_d, rays, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = rtd::launch_trace_rays(s->blob_dev, s->L, s->tri_d_dev, s->stack_entries, rays_d, n, precision == 64, id_d, t_d, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(tri_id, id_d, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(t, t_d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(rays_d); cudaFree(t_d); cudaFree(id_d);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("rt_trace_primary: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_primary_rays(RtScene* s, const int32_t* xy, const double* xi, int64_t n, double* rays_out) {
+    if (!s || !xy || !xi || !rays_out || n < 0) return fail(RT_ERR_INVALID, "bad argument");
+    if (n == 0) return RT_OK;
+    if (!s->blob_dev) return fail(RT_ERR_CUDA, "scene is host-only: no CUDA device bound, there is no CPU fallback");
+    CUDA_TRY(cudaSetDevice(s->device));
+    rtd::Camera cam; fill_camera(s->host, &cam);
+    int32_t* xy_d = nullptr; double *xi_d = nullptr, *r_d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&xy_d, (size_t)n * 2 * sizeof(int32_t)));
+    cudaError_t e = cudaMalloc((void**)&xi_d, (size_t)n * 2 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMalloc((void**)&r_d, (size_t)n * 6 * sizeof(double));
+    if (e == cudaSuccess) e = cudaMemcpyAsync(xy_d, xy, (size_t)n * 2 * sizeof(int32_t), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(xi_d, xi, (size_t)n * 2 * sizeof(double), cudaMemcpyHostToDevice, s->stream);
+    if (e == cudaSuccess) e = rtd::launch_primary_rays(cam, s->host.width, s->host.height, xy_d, xi_d, n, r_d, s->stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(rays_out, r_d, (size_t)n * 6 * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
+    cudaFree(xy_d); cudaFree(xi_d); cudaFree(r_d);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("rt_primary_rays: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+int rt_eval(RtScene* s, int32_t fn, const float* in, int64_t n, float* out) {
+    const int win = rtd::eval_in_width(fn), wout = rtd::eval_out_width(fn);
+    if (win == 0 || !in || !out || n < 0) return fail(RT_ERR_INVALID, "bad argument");
+    const bool needs_scene = fn == RT_FN_PDF_LIGHT || fn == RT_FN_PDF_MIX || fn == RT_FN_SAMPLE_LIGHT;
+    if (needs_scene && !s) return fail(RT_ERR_INVALID, "this function needs a scene");
+    if (s && !s->blob_dev) return fail(RT_ERR_CUDA, "scene is host-only: no CUDA device bound, there is no CPU fallback");
+    if (n == 0) return RT_OK;
+    int count = 0;
+    if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0) return fail(RT_ERR_CUDA, "no CUDA device available (there is no CPU fallback)");
+    if (s) CUDA_TRY(cudaSetDevice(s->device));
+    rtd::SceneLayout L;
+    std::memset(&L, 0, sizeof(L));
+    if (s) L = s->L;
+    float *in_d = nullptr, *out_d = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&in_d, (size_t)n * (size_t)win * sizeof(float)));
+    cudaError_t e = cudaMalloc((void**)&out_d, (size_t)n * (size_t)wout * sizeof(float));
+    cudaStream_t stream = s ? s->stream : (cudaStream_t)0;
+    if (e == cudaSuccess) e = cudaMemcpyAsync(in_d, in, (size_t)n * (size_t)win * sizeof(float), cudaMemcpyHostToDevice, stream);
+    if (e == cudaSuccess) e = rtd::launch_eval(s ? s->blob_dev : nullptr, L, s ? s->stack_entries : 16u, fn, in_d, n, out_d, stream);
+    if (e == cudaSuccess) e = cudaMemcpyAsync(out, out_d, (size_t)n * (size_t)wout * sizeof(float), cudaMemcpyDeviceToHost, stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(stream);
+    cudaFree(in_d); cudaFree(out_d);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("rt_eval: ") + cudaGetErrorString(e));
+    return RT_OK;
+}
+
+// dump_rendered_to_ppm (main.rs:88-95)
+int rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb, int32_t append) {
+    if (!path || !rgb || width <= 0 || height <= 0) return fail(RT_ERR_INVALID, "bad argument");
+    FILE* f = std::fopen(path, append ? "ab" : "wb");
+    if (!f) return fail(RT_ERR_IO, std::string("cannot open ") + path);
+    std::fprintf(f, "P6\n%d %d\n255\n", width, height);
+    const size_t n = (size_t)width * (size_t)height * 3;
+    const bool ok = std::fwrite(rgb, 1, n, f) == n;
+    std::fclose(f);
+    return ok ? RT_OK : fail(RT_ERR_IO, std::string("short write to ") + path);
+}
+
+int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_mhz) {
+    if (!tflops) return fail(RT_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    int sms = 0, khz = 0;
+    CUDA_TRY(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, device));
+    CUDA_TRY(cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, device));
+    float* sink = nullptr;
+    CUDA_TRY(cudaMalloc((void**)&sink, 64));
+    cudaEvent_t e0, e1;
+    CUDA_TRY(cudaEventCreate(&e0)); CUDA_TRY(cudaEventCreate(&e1));
+    const int blocks = sms * 8, threads = 256, iters = 1 << 15;
+    double best = 0.0;
+    cudaError_t e = rtd::launch_ffma(blocks, threads, 1 << 10, sink, 0);
+    for (int rep = 0; rep < 5 && e == cudaSuccess; ++rep) {
+        cudaEventRecord(e0, 0);
+        e = rtd::launch_ffma(blocks, threads, iters, sink, 0);
+        cudaEventRecord(e1, 0);
+        if (e == cudaSuccess) e = cudaEventSynchronize(e1);
+        float ms = 0;
+        cudaEventElapsedTime(&ms, e0, e1);
+        const double flop = 2.0 * 16.0 * (double)iters * (double)threads * (double)blocks;
+        if (ms > 0) best = std::max(best, flop / (ms * 1e-3) / 1e12);
+    }
+    cudaEventDestroy(e0); cudaEventDestroy(e1); cudaFree(sink);
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("ffma benchmark: ") + cudaGetErrorString(e));
+    *tflops = best;
+    if (sm_mhz) *sm_mhz = (double)khz / 1000.0;
+    return RT_OK;
+}
+
+}  // extern "C"
