@@ -130,7 +130,11 @@ RT_DEV bool tri_test(float3 o, float3 d, float3 a, float3 e1, float3 e2, float& 
     u = dot(tvec, pvec) * inv_det;
     v = dot(d, qvec) * inv_det;
     t = dot(e2, qvec) * inv_det;
-    return (u >= 0.0f) & (v >= 0.0f) & (u + v <= 1.0f) & (t > 0.0f);
+    // Edges are inclusive in the reference (f64, effectively watertight).  In FP32 the two triangles sharing an
+    // edge can both round a ray just outside; a 2e-6 barycentric overlap closes those cracks for well-conditioned
+    // triangles (overlap is harmless: the nearest hit still wins).
+    const float tol = 2e-6f;
+    return (u >= -tol) & (v >= -tol) & (u + v <= 1.0f + tol) & (t > 0.0f);
 }
 
 struct Hit { float t, u, v; int tri; };

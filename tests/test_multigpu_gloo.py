@@ -1,0 +1,56 @@
+"""World-size-2 gloo test of the N>1 host logic (no GPU): sample shards partition [0, S) exactly, and the reduce
+of per-rank accumulators to rank 0 equals the sum -- the only collective of the path."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+
+from conftest import ROOT
+
+
+def test_shard_ranges_partition_samples(rt):
+    from raytracing_course_2024_b200 import multigpu
+    for samples in (1, 2, 7, 64, 1000, 1024):
+        for world in (1, 2, 3, 4, 8):
+            r = [multigpu.shard_range(samples, k, world) for k in range(world)]
+            assert r[0][0] == 0 and r[-1][1] == samples
+            assert all(r[k][1] == r[k + 1][0] for k in range(world - 1))
+            sizes = [b - a for a, b in r]
+            assert max(sizes) - min(sizes) <= 1
+
+
+WORKER = r'''
+import os, sys
+sys.path.insert(0, sys.argv[1])
+import numpy as np, torch, torch.distributed as dist
+import rtb200
+from raytracing_course_2024_b200 import multigpu
+dist.init_process_group("gloo", init_method="tcp://127.0.0.1:" + sys.argv[2], rank=int(sys.argv[3]), world_size=2)
+rank = dist.get_rank()
+W, H, S = 16, 8, 10
+lo, hi = multigpu.shard_range(S, rank, 2)
+g = torch.Generator().manual_seed(0)
+per_sample = torch.rand(S, H * W, 3, generator=g, dtype=torch.float32)          # same on both ranks
+acc = torch.zeros(H * W, 4)
+acc[:, :3] = per_sample[lo:hi].sum(0); acc[:, 3] = hi - lo
+multigpu.reduce_to_root(acc, 0)
+if rank == 0:
+    full = per_sample.sum(0)
+    assert torch.allclose(acc[:, :3], full, rtol=1e-6, atol=1e-6), "reduce != sum of shards"
+    assert torch.all(acc[:, 3] == S)
+    print("OK")
+dist.barrier()
+dist.destroy_process_group()
+'''
+
+
+def test_two_rank_gloo_reduce(rt, tmp_path):
+    script = tmp_path / "worker.py"
+    script.write_text(WORKER)
+    port = str(29500 + os.getpid() % 2000)
+    procs = [subprocess.Popen([sys.executable, str(script), ROOT, port, str(r)], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True) for r in range(2)]
+    outs = [p.communicate(timeout=180) for p in procs]
+    for p, (o, e) in zip(procs, outs):
+        assert p.returncode == 0, e
+    assert "OK" in outs[0][0]
