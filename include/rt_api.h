@@ -74,7 +74,9 @@ typedef struct RtRenderParams {
     int32_t sample_begin, sample_end; /* this call renders samples [begin,end) of [0,samples); 0,0 = all  */
     int32_t max_attempts;             /* cap of the rejection loop rendering.rs:102-110 (0 = default 64)  */
     int32_t collect_stats;            /* 1: run the instrumented kernel and fill the work counters         */
-    int32_t kernel_variant;           /* 0 = auto; >0 selects a specific kernel build (benchmarks)        */
+    int32_t kernel_variant;           /* 0 = auto; else 10*kernel + placement (benchmarks / A-B tests):
+                                         kernel 1 = per-lane megakernel, 2 / 3 = warp-local wavefront with 64 / 96 slots per warp;
+                                         placement 1 = scene in global memory, 2 = scene in shared memory   */
     int32_t reserved[3];
 } RtRenderParams;
 

@@ -253,7 +253,7 @@ int ensure(T** p, size_t* cap, size_t need_elems) {
     return RT_OK;
 }
 
-struct RenderPlan { rtd::RenderArgs args; bool use_smem; bool stats; };
+struct RenderPlan { rtd::RenderArgs args; bool use_smem; bool stats; int variant; };
 
 // Shared front half of the three render entry points: launches the path-tracing kernel into s->layers.
 int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, RenderPlan* plan, rtd::KernelInfo* ki) {
@@ -285,13 +285,18 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     a.stack_entries = s->stack_entries;
     a.seed_lo = (uint32_t)(p->seed & 0xffffffffu); a.seed_hi = (uint32_t)(p->seed >> 32);
     plan->stats = p->collect_stats != 0;
+    // kernel_variant = 10*kernel + scene placement: kernel 0 auto (= 2), 1 = v1 per-lane megakernel, 2 = v2 pool of 64 slots
+    // per warp, 3 = v2 pool of 96; placement 0 auto, 1 global memory, 2 shared memory
     plan->use_smem = s->use_smem;
-    if (p->kernel_variant == 1) plan->use_smem = false;
-    if (p->kernel_variant == 2) plan->use_smem = true;
+    const int placement = p->kernel_variant % 10, kern = p->kernel_variant / 10;
+    if (placement == 1) plan->use_smem = false;
+    if (placement == 2) plan->use_smem = true;
+    plan->variant = kern == 0 ? env_int("RT_KERNEL", 2) : kern;
+    if (plan->variant < 1 || plan->variant > 3) return fail(RT_ERR_INVALID, "kernel_variant: unknown kernel");
 
     // sample chunks: enough (pixel, chunk) items to keep every resident lane busy ~4 times over
     int lanes = 0;
-    CUDA_TRY(rtd::render_resident_lanes(plan->use_smem, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
+    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->use_smem, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
     const int n_samp = s1 - s0;
     long long want = (4LL * lanes + a.n_pix_items - 1) / a.n_pix_items;
     if (want < 1) want = 1;
@@ -310,7 +315,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     a.layers = s->layers; a.work_counter = s->work_counter; a.stats = s->stats_dev;
     CUDA_TRY(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
     if (plan->stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, sizeof(unsigned long long) * rtd::RT_N_STATS, stream));
-    CUDA_TRY(rtd::launch_render(a, plan->use_smem, plan->stats, s->sms, stream, ki));
+    CUDA_TRY(rtd::launch_render(a, plan->variant, plan->use_smem, plan->stats, s->sms, stream, ki));
     return RT_OK;
 }
 

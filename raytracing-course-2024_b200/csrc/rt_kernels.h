@@ -33,10 +33,11 @@ enum { RT_STAT_SAMPLES = 0, RT_STAT_SEGMENTS, RT_STAT_VERTICES, RT_STAT_ATTEMPTS
 
 struct KernelInfo { int block, blocks_per_sm, regs, smem_bytes, grid; };
 
-// Launch the persistent render kernel.  use_smem: stage the blob in shared memory.  Returns cudaError_t.
-cudaError_t launch_render(const RenderArgs& a, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info);
+// Launch the persistent render kernel.  variant: 1 = v1 per-lane megakernel, 2 / 3 = v2 warp-local wavefront with 64 / 96
+// path slots per warp.  use_smem: stage the blob in shared memory.  Returns cudaError_t.
+cudaError_t launch_render(const RenderArgs& a, int variant, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info);
 // How many lanes the render kernel keeps resident (grid * block) -- used to size the sample chunks.
-cudaError_t render_resident_lanes(bool use_smem, bool stats, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
+cudaError_t render_resident_lanes(int variant, bool use_smem, bool stats, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
 
 cudaError_t launch_sum_layers(const float4* layers, int n_layers, size_t n_pix, float4* accum, bool add, cudaStream_t stream);
 cudaError_t launch_resolve_u8(const float4* accum, size_t n_pix, uint8_t* rgb, cudaStream_t stream);

@@ -286,6 +286,26 @@ def test_render_u8_matches_oracle_tonemap_and_is_deterministic(gpu_rt, oracle):
     sc.close()
 
 
+def test_kernel_variants_render_the_same_image(gpu_rt):
+    """The per-lane megakernel (v1) and the warp-local wavefront (v2, 64 or 96 slots per warp) evaluate the same
+    estimator with the same Philox counters (pixel, sample, call#): their images must agree to FP32 rounding."""
+    W, H, spp = 96, 64, 128
+    for name in ("practice7_4", "practice7_2"):
+        sc = gpu_rt.Scene.from_gltf(scene_path(name), W, H, spp)
+        ref, st1 = sc.render_linear(seed=21, kernel_variant=10, collect_stats=True)
+        for kv in (20, 30, 21, 22):
+            img, st2 = sc.render_linear(seed=21, kernel_variant=kv, collect_stats=True)
+            for k in ("samples", "segments", "vertices", "attempts"):
+                assert abs(st2[k] - st1[k]) <= 1e-4 * st1[k], (name, kv, k, st1[k], st2[k])
+            assert st2["attempt_cap_hits"] == 0 and st2["nonfinite_samples"] == 0
+            # identical paths except where FP32 contraction differs by an ulp and flips a hit: compare robustly
+            diff = np.abs(img.astype(np.float64) - ref.astype(np.float64))
+            scale = np.abs(ref).mean()
+            assert np.median(diff) <= 1e-5 * scale, (name, kv, float(np.median(diff)), float(scale))
+            assert np.mean(diff) <= 2e-2 * scale, (name, kv, float(np.mean(diff)), float(scale))
+        sc.close()
+
+
 def test_sample_sharding_is_consistent(gpu_rt):
     """8e: rendering samples [0,s) in one call or as disjoint shards accumulated on the device gives the same image up
     to FP32 summation order -- the property the multi-GPU path relies on (counter-based RNG keyed by sample index)."""

@@ -20,7 +20,7 @@ ap.add_argument("--height", type=int, default=1080)
 ap.add_argument("--spp", type=int, default=256)
 ap.add_argument("--leaf", default="1,2,4")
 ap.add_argument("--cost", default="0.5,1.0,2.0")
-ap.add_argument("--variants", default="0")
+ap.add_argument("--variants", default="10,20,30")
 ap.add_argument("--reps", type=int, default=3)
 a = ap.parse_args()
 path = os.path.join(ROOT, "scenes", a.scene + ".gltf")
