@@ -200,9 +200,7 @@ int flatten_scene(RtScene* s) {
     L.n_lnodes = s->light_bvh.n_nodes; L.light_bvh = use_light_bvh ? 1 : 0;
 
     const int need = std::max(s->bvh.depth, s->light_bvh.depth) + 2;
-    if (need <= 16) s->stack_entries = 16;
-    else if (need <= 32) s->stack_entries = 32;
-    else if (need <= 64) s->stack_entries = 64;
+    if (need <= 64) s->stack_entries = (uint32_t)std::max(8, (need + 3) / 4 * 4);
     else return fail(RT_ERR_LIMIT, "BVH depth " + std::to_string(need - 2) + " exceeds the 62-entry traversal stack");
     const int smem_limit = env_int("RT_SMEM_SCENE_MAX_BYTES", 48 * 1024);
     s->use_smem = (int)L.total_bytes <= smem_limit;
@@ -253,7 +251,7 @@ int ensure(T** p, size_t* cap, size_t need_elems) {
     return RT_OK;
 }
 
-struct RenderPlan { rtd::RenderArgs args; bool use_smem; bool stats; int variant; };
+struct RenderPlan { rtd::RenderArgs args; bool use_smem; bool stats; int variant; int cfg; };
 
 // Shared front half of the three render entry points: launches the path-tracing kernel into s->layers.
 int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, RenderPlan* plan, rtd::KernelInfo* ki) {
@@ -283,10 +281,12 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     const uint32_t tiles_y = (uint32_t)((h.height + 3) / 4);
     a.n_pix_items = a.tiles_x * tiles_y * 32u;
     a.stack_entries = s->stack_entries;
+    a.node_min = std::min(32, std::max(1, env_int("RT_NODE_MIN", 16)));
+    a.burst_exit = std::min(32, std::max(1, env_int("RT_BURST_EXIT", 8)));
     a.seed_lo = (uint32_t)(p->seed & 0xffffffffu); a.seed_hi = (uint32_t)(p->seed >> 32);
     plan->stats = p->collect_stats != 0;
-    // kernel_variant = 10*kernel + scene placement: kernel 0 auto (= 2), 1 = v1 per-lane megakernel, 2 = v2 pool of 64 slots
-    // per warp, 3 = v2 pool of 96; placement 0 auto, 1 global memory, 2 shared memory
+    // kernel_variant = 10*kernel + scene placement: kernel 0 auto (= 2), 1 = v1 per-lane megakernel, 2 / 3 = v3 warp-local
+    // wavefront with while-while / phased trace bursts; placement 0 auto, 1 global memory, 2 shared memory
     plan->use_smem = s->use_smem;
     const int placement = p->kernel_variant % 10, kern = p->kernel_variant / 10;
     if (placement == 1) plan->use_smem = false;
@@ -294,9 +294,10 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     plan->variant = kern == 0 ? env_int("RT_KERNEL", 2) : kern;
     if (plan->variant < 1 || plan->variant > 3) return fail(RT_ERR_INVALID, "kernel_variant: unknown kernel");
 
+    plan->cfg = env_int("RT_WAVE_CFG", 0);
     // sample chunks: enough (pixel, chunk) items to keep every resident lane busy ~4 times over
     int lanes = 0;
-    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->use_smem, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
+    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
     const int n_samp = s1 - s0;
     long long want = (4LL * lanes + a.n_pix_items - 1) / a.n_pix_items;
     if (want < 1) want = 1;
@@ -315,7 +316,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     a.layers = s->layers; a.work_counter = s->work_counter; a.stats = s->stats_dev;
     CUDA_TRY(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
     if (plan->stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, sizeof(unsigned long long) * rtd::RT_N_STATS, stream));
-    CUDA_TRY(rtd::launch_render(a, plan->variant, plan->use_smem, plan->stats, s->sms, stream, ki));
+    CUDA_TRY(rtd::launch_render(a, plan->variant, plan->cfg, plan->use_smem, plan->stats, s->sms, stream, ki));
     return RT_OK;
 }
 

@@ -249,26 +249,36 @@ static cudaError_t launch_render_t(const RenderArgs& a, int device_sms, cudaStre
     return cudaGetLastError();
 }
 
-#include "rt_render_pool.cuh"
+#include "rt_render_wave.cuh"
 
-// variant: 1 = v1 per-lane megakernel, 2 = v2 pool with 64 slots per warp, 3 = v2 pool with 96 slots per warp
-static cudaError_t dispatch_render(const RenderArgs& a, int variant, bool use_smem, bool stats, int sms, cudaStream_t s, KernelInfo* info, bool launch, int* lanes) {
+// variant: 1 = v1 per-lane megakernel, 2 = v3 warp-local wavefront with while-while bursts, 3 = v3 with phased bursts.
+// cfg (v3 only): resident-thread configuration, see wave_cfg_name().
+static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int sms, cudaStream_t s, KernelInfo* info, bool launch, int* lanes) {
 #define RT_DISPATCH(FN, ...)                                                                                                   \
     (use_smem ? (stats ? FN<SmemSpace, true __VA_ARGS__>(a, sms, s, info, launch, lanes) : FN<SmemSpace, false __VA_ARGS__>(a, sms, s, info, launch, lanes)) \
               : (stats ? FN<GmemSpace, true __VA_ARGS__>(a, sms, s, info, launch, lanes) : FN<GmemSpace, false __VA_ARGS__>(a, sms, s, info, launch, lanes)))
+#define RT_WAVE(MODE)                                                     \
+    switch (cfg) {                                                        \
+        case 1: return RT_DISPATCH(launch_wave_t, , MODE, 256, 3);        \
+        case 2: return RT_DISPATCH(launch_wave_t, , MODE, 384, 2);        \
+        case 3: return RT_DISPATCH(launch_wave_t, , MODE, 256, 4);        \
+        case 4: return RT_DISPATCH(launch_wave_t, , MODE, 512, 2);        \
+        default: return RT_DISPATCH(launch_wave_t, , MODE, 256, 2);       \
+    }
     if (variant == 1) return RT_DISPATCH(launch_render_t);
-    if (variant == 3) return RT_DISPATCH(launch_pool_t, , 96);
-    return RT_DISPATCH(launch_pool_t, , 64);
+    if (variant == 3) { RT_WAVE(1) }
+    RT_WAVE(0)
+#undef RT_WAVE
 #undef RT_DISPATCH
 }
-cudaError_t launch_render(const RenderArgs& a, int variant, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info) {
-    return dispatch_render(a, variant, use_smem, stats, device_sms, stream, info, true, nullptr);
+cudaError_t launch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info) {
+    return dispatch_render(a, variant, cfg, use_smem, stats, device_sms, stream, info, true, nullptr);
 }
-cudaError_t render_resident_lanes(int variant, bool use_smem, bool stats, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes) {
+cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes) {
     RenderArgs a;
     memset(&a, 0, sizeof(a));
     a.L.total_bytes = blob_bytes; a.stack_entries = stack_entries;
-    return dispatch_render(a, variant, use_smem, stats, device_sms, 0, nullptr, false, lanes);
+    return dispatch_render(a, variant, cfg, use_smem, stats, device_sms, 0, nullptr, false, lanes);
 }
 
 // ------------------------------------------------------------------------------------------------ resolve kernels

@@ -22,6 +22,8 @@ struct RenderArgs {
     int32_t s_begin, s_end, chunk_size, n_chunks;
     uint32_t tiles_x, n_pix_items, total_items;
     uint32_t stack_entries;
+    int32_t node_min;            // v3 phased bursts: box-pair steps run while at least this many lanes want one
+    int32_t burst_exit;          // v3: a trace burst ends when this many lanes of the warp have finished their ray (1..32)
     uint32_t seed_lo, seed_hi;
     float4* layers;              // n_chunks x W*H  (rgb sums, sample count)
     unsigned int* work_counter;  // zeroed before launch
@@ -33,11 +35,11 @@ enum { RT_STAT_SAMPLES = 0, RT_STAT_SEGMENTS, RT_STAT_VERTICES, RT_STAT_ATTEMPTS
 
 struct KernelInfo { int block, blocks_per_sm, regs, smem_bytes, grid; };
 
-// Launch the persistent render kernel.  variant: 1 = v1 per-lane megakernel, 2 / 3 = v2 warp-local wavefront with 64 / 96
-// path slots per warp.  use_smem: stage the blob in shared memory.  Returns cudaError_t.
-cudaError_t launch_render(const RenderArgs& a, int variant, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info);
+// Launch the persistent render kernel.  variant: 1 = v1 per-lane megakernel, 2 / 3 = v3 warp-local wavefront (64 path slots per warp) with
+// while-while / phased trace bursts; cfg picks the v3 build (block size x min blocks per SM).  use_smem: stage the blob in shared memory.  Returns cudaError_t.
+cudaError_t launch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info);
 // How many lanes the render kernel keeps resident (grid * block) -- used to size the sample chunks.
-cudaError_t render_resident_lanes(int variant, bool use_smem, bool stats, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
+cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
 
 cudaError_t launch_sum_layers(const float4* layers, int n_layers, size_t n_pix, float4* accum, bool add, cudaStream_t stream);
 cudaError_t launch_resolve_u8(const float4* accum, size_t n_pix, uint8_t* rgb, cudaStream_t stream);

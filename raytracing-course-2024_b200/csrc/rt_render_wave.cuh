@@ -1,0 +1,370 @@
+// rt_render_wave.cuh -- render kernel v3: the warp-local wavefront with burst traversal.  Included by rt_kernels.cu
+// after the shading helpers (DirTerms, mix_sample_and_pdf, camera_ray, load_material, SpaceMaker, IsSmem).
+//
+// ncu of v1 (profiles/r1_v1_*): 31 % warp execution efficiency -- the node loop issues 45 % of all instructions at
+// 8.3/32 active lanes, the leaf loop 17 % at 10.3/32 and shading 38 % at ~10/32, because every lane owns ONE path and
+// the warp waits for its slowest ray / its unluckiest rejection in every iteration.  v2 (a pool whose queues were
+// serviced after EVERY traversal step, profiles/r1_v2b_*) reached 17.7/32 lanes but doubled the thread-instruction
+// count with ballots and queue arithmetic.  v3 keeps the pool and moves the bookkeeping out of the inner loop:
+//   * every warp owns a POOL of 64 path slots in shared memory (SoA, 21 words per slot) and two ring queues over them:
+//     TQ (slots holding a ray to trace) and SQ (slots waiting for shading);
+//   * TRACE BURST: the 32 lanes hold 32 rays in registers and run a plain while-while traversal; after every leaf
+//     phase ONE ballot counts the lanes whose ray is finished, and the burst ends when that count reaches
+//     `burst_exit`.  Finished lanes write (triangle, u, v) to their slot, push it on SQ and pop the next ray of TQ;
+//   * SHADE ROUND: whenever TQ cannot feed the idle lanes, 32 slots of SQ are shaded with all 32 lanes busy (the
+//     in-flight traversals of the other slots stay in registers): finished items are stored and replaced, ended
+//     paths regenerated, and every hit makes exactly ONE attempt of the reference's rejection loop
+//     (rendering.rs:102-110); accepted directions go to TQ, rejected slots return to SQ and retry in a later round.
+//     With 64 slots and 32 lanes, an empty TQ implies >= 32 slots on SQ, so rounds are always full until the frame's
+//     work counter runs dry.
+// Same estimator, same Philox counters (pixel, sample, call#) as v1 -> same image.
+#pragma once
+
+#define RT_POOL_SLOTS 64
+enum { F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_SKIP, F_TRI, F_U, F_V, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ, F_PIX, F_S, F_SSTOP, F_CHUNK, F_META, F_TQ, F_SQ, NF };
+enum { ST_NEED_ITEM = 0, ST_NEED_PATH = 1, ST_GEN = 2, ST_TRACE = 3, ST_RETRY = 4, ST_EXHAUSTED = 5, ST_NONE = 6 };
+#define RT_CUR_DONE ((int)0x80000000)
+
+struct Pool {
+    uint32_t base;
+    RT_DEV uint32_t at(int f, int s) const { return base + (uint32_t)(f * RT_POOL_SLOTS + s) * 4u; }
+    RT_DEV float ldf(int f, int s) const { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(at(f, s))); return v; }
+    RT_DEV int ldi(int f, int s) const { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(at(f, s))); return v; }
+    RT_DEV void stf(int f, int s, float v) const { asm volatile("st.shared.f32 [%0], %1;" ::"r"(at(f, s)), "f"(v)); }
+    RT_DEV void sti(int f, int s, int v) const { asm volatile("st.shared.s32 [%0], %1;" ::"r"(at(f, s)), "r"(v)); }
+    RT_DEV float3 ld3(int f, int s) const { return f3(ldf(f, s), ldf(f + 1, s), ldf(f + 2, s)); }
+    RT_DEV void st3(int f, int s, float3 v) const { stf(f, s, v.x); stf(f + 1, s, v.y); stf(f + 2, s, v.z); }
+};
+// meta word of a slot: state (3 bits) | segments left (8) | attempts made at this vertex (7) | Philox call counter (14)
+RT_DEV uint32_t pack_meta(int state, int depth, int attempt, uint32_t call) { return (uint32_t)state | ((uint32_t)depth << 3) | ((uint32_t)attempt << 11) | (call << 18); }
+
+// MODE 0: while-while burst.  MODE 1: phased burst (box-pair steps while >= node_min lanes want one, else leaf phase).
+// BLOCK x MINB = resident threads per SM (occupancy / register budget trade-off, picked at run time from a few builds).
+template <class Space, bool STATS, int MODE, int BLOCK, int MINB>
+__global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderArgs a) {
+    constexpr int P = RT_POOL_SLOTS;
+    extern __shared__ __align__(16) unsigned char smem_raw[];
+    const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
+    const uint32_t stack_bytes = a.stack_entries * blockDim.x * 4u;
+    const uint32_t blob_bytes = IsSmem<Space>::value ? a.L.total_bytes : 0u;
+    if (IsSmem<Space>::value) {
+        const uint4* src = reinterpret_cast<const uint4*>(a.blob);
+        uint4* dst = reinterpret_cast<uint4*>(smem_raw + stack_bytes);
+        for (uint32_t i = threadIdx.x; i < a.L.total_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
+        __syncthreads();
+    }
+    const Space sp = SpaceMaker<Space>::make(a.blob, smem_base + stack_bytes);
+    const SceneLayout& L = a.L;
+    SmemStack st; st.addr = smem_base + threadIdx.x * 4u; st.stride = blockDim.x * 4u;
+    const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    const unsigned lt_mask = (1u << lane) - 1u;
+    const unsigned FULL = 0xffffffffu;
+    Pool pool; pool.base = smem_base + stack_bytes + blob_bytes + warp * (uint32_t)(P * NF * 4);
+    const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
+    const float3 bg = f3(a.bg[0], a.bg[1], a.bg[2]);
+    const bool bg_nonzero = (a.bg[0] != 0.f) | (a.bg[1] != 0.f) | (a.bg[2] != 0.f);
+    const size_t n_pix = (size_t)a.W * (size_t)a.H;
+    const int burst_exit = a.burst_exit, node_min = a.node_min;
+
+    Counters cnt; cnt.node_tests = 0; cnt.tri_tests = 0; cnt.light_tri_tests = 0;
+    unsigned long long c_samples = 0, c_segments = 0, c_vertices = 0, c_attempts = 0, c_cap = 0, c_nonfinite = 0;
+
+    // ring queues: positions in [0, P), counts separate (all warp-uniform)
+    int tq_head = 0, tq_n = 0, sq_head = 0, sq_n = P;
+    for (int s = (int)lane; s < P; s += 32) { pool.sti(F_META, s, (int)pack_meta(ST_NEED_ITEM, 0, 0, 0u)); pool.sti(F_SQ, s, s); }
+    __syncwarp();
+
+    // traversal state of this lane's in-flight ray
+    int slot = -1, cur = RT_CUR_DONE, sptr = 0, skip_tri = -1;
+    float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f), inv = f3(1.f, 1.f, 1.f), od = f3(0.f, 0.f, 0.f);
+    Hit hit; hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
+
+    for (;;) {
+        // ---------------------------------------------------------------------------------- retire finished rays, refill from TQ
+        {
+            const bool finished = slot >= 0 && cur == RT_CUR_DONE;
+            const unsigned fin = __ballot_sync(FULL, finished);
+            if (fin != 0u) {
+                if (finished) {
+                    pool.sti(F_TRI, slot, hit.tri); pool.stf(F_U, slot, hit.u); pool.stf(F_V, slot, hit.v);
+                    pool.sti(F_SQ, (sq_head + sq_n + __popc(fin & lt_mask)) & (P - 1), slot);
+                    slot = -1;
+                }
+                sq_n += __popc(fin);
+            }
+            const unsigned idle = __ballot_sync(FULL, slot < 0);
+            const int n_idle = __popc(idle);
+            if (n_idle > 0 && tq_n > 0) {
+                const int rank = __popc(idle & lt_mask);
+                if (slot < 0 && rank < tq_n) {
+                    slot = pool.ldi(F_TQ, (tq_head + rank) & (P - 1));
+                    o = pool.ld3(F_OX, slot); d = pool.ld3(F_DX, slot);
+                    skip_tri = pool.ldi(F_SKIP, slot);
+                    inv = safe_inv_dir(d); od = o * inv;
+                    hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
+                    cur = 0; sptr = 0;
+                    if (STATS) ++c_segments;
+                }
+                const int took = min(n_idle, tq_n);
+                tq_head = (tq_head + took) & (P - 1);
+                tq_n -= took;
+            }
+            __syncwarp();
+            // ------------------------------------------------------------------------------ shade round when TQ ran dry
+            if (n_idle > 0 && tq_n == 0 && sq_n > 0 && __ballot_sync(FULL, slot < 0) != 0u) {
+                const int n_take = min(32, sq_n);
+                int s = 0, state = ST_NONE;
+                uint32_t meta = 0;
+                if ((int)lane < n_take) {
+                    s = pool.ldi(F_SQ, (sq_head + (int)lane) & (P - 1));
+                    meta = (uint32_t)pool.ldi(F_META, s);
+                    state = (int)(meta & 7u);
+                }
+                sq_head = (sq_head + n_take) & (P - 1);
+                sq_n -= n_take;
+                if (state == ST_TRACE || state == ST_RETRY) {                    // get_ray_color (rendering.rs:86-127), one attempt
+                    int depth = (int)((meta >> 3) & 0xffu), attempt = (int)((meta >> 11) & 0x7fu);
+                    uint32_t call = meta >> 18;
+                    const int tri = pool.ldi(F_TRI, s);
+                    float3 T = pool.ld3(F_TX, s);
+                    bool end_path = false;
+                    if (tri < 0) {                                               // :125
+                        if (bg_nonzero) pool.st3(F_AX, s, pool.ld3(F_AX, s) + T * bg);
+                        end_path = true;
+                    } else {
+                        const uint32_t o16 = (uint32_t)tri * 16u;
+                        const float4 n0 = sp.ld4(L.sh_n0 + o16);
+                        const Material mat = load_material(sp, L, __float_as_int(n0.w));
+                        if (attempt == 0) {
+                            if ((mat.emission.x != 0.f) | (mat.emission.y != 0.f) | (mat.emission.z != 0.f))
+                                pool.st3(F_AX, s, pool.ld3(F_AX, s) + T * mat.emission);   // :99
+                            if (--depth <= 0) end_path = true;                   // :93-95
+                            else if (STATS) ++c_vertices;
+                        }
+                        if (!end_path) {
+                            const float3 rd = pool.ld3(F_DX, s);
+                            const float hu = pool.ldf(F_U, s), hv = pool.ldf(F_V, s);
+                            const float3 ng = f3(sp.ld4(L.sh_ng + o16));
+                            const float sgn = dot(ng, rd) < 0.0f ? 1.0f : -1.0f; // geometry.rs:115-126
+                            const float3 n = ng * sgn;
+                            const float3 dn1 = f3(sp.ld4(L.sh_dn1 + o16)), dn2 = f3(sp.ld4(L.sh_dn2 + o16));
+                            const float3 ns = (f3(n0) + dn1 * hu + dn2 * hv) * sgn;
+                            const float3 ta = f3(sp.ld4(L.tri_a + o16)), te1 = f3(sp.ld4(L.tri_e1 + o16)), te2 = f3(sp.ld4(L.tri_e2 + o16));
+                            const float3 Pt = fma3(rd, -RT_EPS_F, fma3(te2, hv, fma3(te1, hu, ta)));   // :98
+                            const float3 v = -rd;
+                            const float nv = dot(n, v);
+                            const float alpha = mat.roughness * mat.roughness, alpha2 = alpha * alpha;
+                            const float g1v = ggx_g1(nv, alpha2);
+                            const uint32_t pix = (uint32_t)pool.ldi(F_PIX, s);
+                            const int s_this = pool.ldi(F_S, s);
+                            const uint4 rnd = philox4x32_10(make_uint4(pix, (uint32_t)s_this, call, RT_PHILOX_TAG), key);
+                            call = (call + 1u) & 0x3fffu;
+                            float3 l; DirTerms terms;
+                            const float pdf = mix_sample_and_pdf<Space, STATS>(sp, L, st, a.n_comp, Pt, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
+                            ++attempt;
+                            if (STATS) ++c_attempts;
+                            if (pdf > 0.0f && dot(l, ns) > 0.0f) {               // :107
+                                const float d_chi = terms.nh > 0.0f ? terms.d_nochi : 0.0f;
+                                const float3 f = brdf_eval(mat, d_chi, ggx_g1(terms.nl, alpha2), g1v, terms.nl, nv, terms.hl);
+                                T = T * f * (terms.nl * fast_rcp(pdf));          // :122
+                                if (!finite3(T)) { if (STATS) ++c_nonfinite; end_path = true; }
+                                else {
+                                    pool.st3(F_OX, s, Pt); pool.st3(F_DX, s, l); pool.st3(F_TX, s, T);
+                                    pool.sti(F_SKIP, s, terms.nl > 0.0f ? tri : -1);
+                                    attempt = 0; state = ST_TRACE;
+                                }
+                            } else if (attempt >= a.max_attempts || attempt >= 127) {
+                                if (STATS) ++c_cap;
+                                end_path = true;
+                            } else {
+                                state = ST_RETRY;
+                            }
+                        }
+                    }
+                    if (end_path) state = ST_NEED_PATH;
+                    meta = pack_meta(state, depth, attempt, call);
+                }
+                if (state == ST_NEED_PATH) {                                     // next sample of this item, or store the item
+                    const int s_next = pool.ldi(F_S, s) + 1, s_stop = pool.ldi(F_SSTOP, s);
+                    if (s_next < s_stop) { pool.sti(F_S, s, s_next); state = ST_GEN; }
+                    else {
+                        const int chunk = pool.ldi(F_CHUNK, s);
+                        const uint32_t pix = (uint32_t)pool.ldi(F_PIX, s);
+                        const float3 acc = pool.ld3(F_AX, s);
+                        const float n_done = (float)(s_stop - (a.s_begin + chunk * a.chunk_size));
+                        a.layers[(size_t)chunk * n_pix + pix] = make_float4(acc.x, acc.y, acc.z, n_done);
+                        state = ST_NEED_ITEM;
+                    }
+                }
+                for (;;) {                                                       // warp-aggregated work fetch
+                    const bool need = state == ST_NEED_ITEM;
+                    const unsigned m = __ballot_sync(FULL, need);
+                    if (m == 0u) break;
+                    const int leader = __ffs(m) - 1;
+                    unsigned int base = 0;
+                    if ((int)lane == leader) base = atomicAdd(a.work_counter, (unsigned int)__popc(m));
+                    base = __shfl_sync(FULL, base, leader);
+                    if (need) {
+                        const uint32_t idx = base + (uint32_t)__popc(m & lt_mask);
+                        if (idx >= a.total_items) state = ST_EXHAUSTED;
+                        else {
+                            const uint32_t chunk = idx / a.n_pix_items;
+                            const uint32_t rr = idx - chunk * a.n_pix_items;
+                            const uint32_t tile = rr >> 5, w = rr & 31u;
+                            const uint32_t ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
+                            const int px = (int)(tx * 8u + (w & 7u)), py = (int)(ty * 4u + (w >> 3));
+                            if (px < a.W && py < a.H) {
+                                const int s0 = a.s_begin + (int)chunk * a.chunk_size;
+                                pool.sti(F_PIX, s, (int)((uint32_t)py * (uint32_t)a.W + (uint32_t)px));
+                                pool.sti(F_CHUNK, s, (int)chunk);
+                                pool.sti(F_S, s, s0);
+                                pool.sti(F_SSTOP, s, min(s0 + a.chunk_size, a.s_end));
+                                pool.st3(F_AX, s, f3(0.f, 0.f, 0.f));
+                                state = ST_GEN;
+                            }
+                        }
+                    }
+                }
+                if (state == ST_GEN) {                                           // get_ray_to_pixel (rendering.rs:71-84)
+                    const uint32_t pix = (uint32_t)pool.ldi(F_PIX, s);
+                    const int s_this = pool.ldi(F_S, s);
+                    const int py = (int)(pix / (uint32_t)a.W), px = (int)(pix - (uint32_t)py * (uint32_t)a.W);
+                    const uint4 rr = philox4x32_10(make_uint4(pix, (uint32_t)s_this, 0u, RT_PHILOX_TAG), key);
+                    float3 co, cd;
+                    camera_ray(a.cam, a.W, a.H, px, py, u01(rr.x), u01(rr.y), co, cd);
+                    pool.st3(F_OX, s, co); pool.st3(F_DX, s, cd); pool.st3(F_TX, s, f3(1.f, 1.f, 1.f));
+                    pool.sti(F_SKIP, s, -1);
+                    state = ST_TRACE;
+                    meta = pack_meta(state, a.ray_depth > 255 ? 255 : a.ray_depth, 0, 1u);
+                    if (STATS) ++c_samples;
+                } else {
+                    meta = (meta & ~7u) | (uint32_t)state;
+                }
+                if (state != ST_NONE) pool.sti(F_META, s, (int)meta);
+                const unsigned to_tq = __ballot_sync(FULL, state == ST_TRACE);
+                if (state == ST_TRACE) pool.sti(F_TQ, (tq_head + tq_n + __popc(to_tq & lt_mask)) & (P - 1), s);
+                tq_n += __popc(to_tq);
+                const unsigned to_sq = __ballot_sync(FULL, state == ST_RETRY);   // rejected attempt: retry in a later round
+                if (state == ST_RETRY) pool.sti(F_SQ, (sq_head + sq_n + __popc(to_sq & lt_mask)) & (P - 1), s);
+                sq_n += __popc(to_sq);
+                __syncwarp();
+                continue;
+            }
+        }
+        if (__ballot_sync(FULL, slot >= 0) == 0u) break;                         // nothing in flight, nothing queued: pool exhausted
+
+        // ---------------------------------------------------------------------------------- trace burst
+        if (MODE == 0) {
+            for (;;) {
+                while (cur >= 0) {
+                    const uint32_t o16 = (uint32_t)cur * 16u;
+                    const float4 A = sp.ld4(L.box_a + o16), B = sp.ld4(L.box_b + o16), C = sp.ld4(L.box_c + o16);
+                    const int2 ch = sp.ld2i(L.child + (uint32_t)cur * 8u);
+                    float t0, t1;
+                    const bool h0 = slab(A.x, A.y, A.z, A.w, C.x, C.y, inv, od, hit.t, t0);
+                    const bool h1 = slab(B.x, B.y, B.z, B.w, C.z, C.w, inv, od, hit.t, t1);
+                    if (STATS) cnt.node_tests += 2;
+                    if (h0 & h1) {
+                        const bool swap = t1 < t0;
+                        st.store(sptr++, swap ? ch.x : ch.y);
+                        cur = swap ? ch.y : ch.x;
+                    } else if (h0 | h1) {
+                        cur = h0 ? ch.x : ch.y;
+                    } else {
+                        cur = sptr == 0 ? RT_CUR_DONE : st.load(--sptr);
+                    }
+                }
+                if (cur != RT_CUR_DONE) {
+                    const uint32_t code = (uint32_t)~cur;
+                    const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
+                    for (int i = first; i < first + n; ++i) {
+                        const uint32_t o16 = (uint32_t)i * 16u;
+                        const float4 ta = sp.ld4(L.tri_a + o16), e1 = sp.ld4(L.tri_e1 + o16), e2 = sp.ld4(L.tri_e2 + o16);
+                        float t, u, v;
+                        const bool ok = tri_test(o, d, f3(ta), f3(e1), f3(e2), t, u, v);
+                        if (STATS) cnt.tri_tests += 1;
+                        if (ok && t < hit.t && i != skip_tri) { hit.t = t; hit.u = u; hit.v = v; hit.tri = i; }
+                    }
+                    cur = sptr == 0 ? RT_CUR_DONE : st.load(--sptr);
+                }
+                if (__popc(__ballot_sync(FULL, cur == RT_CUR_DONE)) >= burst_exit) break;
+            }
+        } else {
+            // phased burst: box-pair steps run while at least `node_min` lanes want one; otherwise the lanes that sit on a
+            // leaf test its triangles; the minority keeps its state and waits for its phase.
+            for (bool progressed = false;; progressed = true) {
+                const int nn = __popc(__ballot_sync(FULL, cur >= 0));
+                bool node_step = nn >= node_min;
+                if (!node_step) {
+                    const bool at_leaf = cur < 0 && cur != RT_CUR_DONE;
+                    if (__ballot_sync(FULL, at_leaf) != 0u) {
+                        if (at_leaf) {
+                            const uint32_t code = (uint32_t)~cur;
+                            const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
+                            for (int i = first; i < first + n; ++i) {
+                                const uint32_t o16 = (uint32_t)i * 16u;
+                                const float4 ta = sp.ld4(L.tri_a + o16), e1 = sp.ld4(L.tri_e1 + o16), e2 = sp.ld4(L.tri_e2 + o16);
+                                float t, u, v;
+                                const bool ok = tri_test(o, d, f3(ta), f3(e1), f3(e2), t, u, v);
+                                if (STATS) cnt.tri_tests += 1;
+                                if (ok && t < hit.t && i != skip_tri) { hit.t = t; hit.u = u; hit.v = v; hit.tri = i; }
+                            }
+                            cur = sptr == 0 ? RT_CUR_DONE : st.load(--sptr);
+                        }
+                        if (__popc(__ballot_sync(FULL, cur == RT_CUR_DONE)) >= burst_exit) break;
+                        continue;
+                    }
+                    if (nn == 0 || (progressed && 32 - nn >= burst_exit)) break;  // only box-pair lanes and finished lanes are left
+                    node_step = true;
+                }
+                if (cur >= 0) {
+                    const uint32_t o16 = (uint32_t)cur * 16u;
+                    const float4 A = sp.ld4(L.box_a + o16), B = sp.ld4(L.box_b + o16), C = sp.ld4(L.box_c + o16);
+                    const int2 ch = sp.ld2i(L.child + (uint32_t)cur * 8u);
+                    float t0, t1;
+                    const bool h0 = slab(A.x, A.y, A.z, A.w, C.x, C.y, inv, od, hit.t, t0);
+                    const bool h1 = slab(B.x, B.y, B.z, B.w, C.z, C.w, inv, od, hit.t, t1);
+                    if (STATS) cnt.node_tests += 2;
+                    if (h0 & h1) {
+                        const bool swap = t1 < t0;
+                        st.store(sptr++, swap ? ch.x : ch.y);
+                        cur = swap ? ch.y : ch.x;
+                    } else if (h0 | h1) {
+                        cur = h0 ? ch.x : ch.y;
+                    } else {
+                        cur = sptr == 0 ? RT_CUR_DONE : st.load(--sptr);
+                    }
+                }
+            }
+        }
+    }
+    if (STATS) {
+        atomicAdd(a.stats + RT_STAT_SAMPLES, c_samples); atomicAdd(a.stats + RT_STAT_SEGMENTS, c_segments);
+        atomicAdd(a.stats + RT_STAT_VERTICES, c_vertices); atomicAdd(a.stats + RT_STAT_ATTEMPTS, c_attempts);
+        atomicAdd(a.stats + RT_STAT_NODE_TESTS, cnt.node_tests); atomicAdd(a.stats + RT_STAT_TRI_TESTS, cnt.tri_tests);
+        atomicAdd(a.stats + RT_STAT_LIGHT_TRI_TESTS, cnt.light_tri_tests); atomicAdd(a.stats + RT_STAT_CAP_HITS, c_cap);
+        atomicAdd(a.stats + RT_STAT_NONFINITE, c_nonfinite);
+    }
+}
+
+template <class Space, bool STATS, int MODE, int BLOCK, int MINB>
+static cudaError_t launch_wave_t(const RenderArgs& a, int device_sms, cudaStream_t stream, KernelInfo* info, bool launch, int* lanes) {
+    const uint32_t smem = a.stack_entries * BLOCK * 4u + (IsSmem<Space>::value ? a.L.total_bytes : 0u) + (BLOCK / 32) * (uint32_t)(RT_POOL_SLOTS * NF * 4);
+    auto kern = render_wave_kernel<Space, STATS, MODE, BLOCK, MINB>;
+    cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    if (e != cudaSuccess) return e;
+    int per_sm = 0;
+    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, BLOCK, smem);
+    if (e != cudaSuccess) return e;
+    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+    const int grid = per_sm * device_sms;
+    if (lanes) *lanes = grid * (BLOCK / 32) * RT_POOL_SLOTS;       // resident path slots
+    if (info) {
+        cudaFuncAttributes fa;
+        cudaFuncGetAttributes(&fa, kern);
+        info->block = BLOCK; info->blocks_per_sm = per_sm; info->regs = fa.numRegs; info->smem_bytes = (int)smem; info->grid = grid;
+    }
+    if (!launch) return cudaSuccess;
+    kern<<<grid, BLOCK, smem, stream>>>(a);
+    return cudaGetLastError();
+}

@@ -293,7 +293,7 @@ def test_kernel_variants_render_the_same_image(gpu_rt):
     for name in ("practice7_4", "practice7_2"):
         sc = gpu_rt.Scene.from_gltf(scene_path(name), W, H, spp)
         ref, st1 = sc.render_linear(seed=21, kernel_variant=10, collect_stats=True)
-        for kv in (20, 30, 21, 22):
+        for kv in (20, 30, 21) + ((22,) if name == "practice7_4" else ()):   # placement 2 = shared memory: small scenes only
             img, st2 = sc.render_linear(seed=21, kernel_variant=kv, collect_stats=True)
             for k in ("samples", "segments", "vertices", "attempts"):
                 assert abs(st2[k] - st1[k]) <= 1e-4 * st1[k], (name, kv, k, st1[k], st2[k])
