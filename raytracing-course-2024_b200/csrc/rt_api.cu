@@ -66,6 +66,28 @@ struct BlobWriter {
 
 inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
 
+// FlatBvh (box_a/box_b/box_c/child, host_scene.h) -> the device's octant-ordered pair nodes (rt_device.cuh, RT_NODE_BYTES):
+// per axis (c0.min c1.min c0.max c1.max | c0.max c1.max c0.min c1.min), then the two child references.
+std::vector<float> octant_nodes(const rtb::FlatBvh& b) {
+    const size_t wpn = RT_NODE_BYTES / 4;
+    std::vector<float> out((size_t)std::max(b.n_nodes, 1) * wpn, 0.f);
+    for (int n = 0; n < b.n_nodes; ++n) {
+        const float* A = &b.box_a[(size_t)n * 4]; const float* B = &b.box_b[(size_t)n * 4]; const float* C = &b.box_c[(size_t)n * 4];
+        const float lo0[3] = {A[0], A[2], C[0]}, hi0[3] = {A[1], A[3], C[1]}, lo1[3] = {B[0], B[2], C[2]}, hi1[3] = {B[1], B[3], C[3]};
+        float* o = &out[(size_t)n * wpn];
+        for (int a = 0; a < 3; ++a) {
+            float* q = o + a * 8;
+            q[0] = lo0[a]; q[1] = lo1[a]; q[2] = hi0[a]; q[3] = hi1[a];
+            q[4] = hi0[a]; q[5] = hi1[a]; q[6] = lo0[a]; q[7] = lo1[a];
+        }
+        for (int c = 0; c < 2; ++c) {      // inner children as byte offsets (index * RT_NODE_BYTES), leaf codes unchanged
+            const int32_t r = b.child[(size_t)n * 2 + (size_t)c];
+            o[24 + c] = i2f(r >= 0 ? r * (int32_t)RT_NODE_BYTES : r);
+        }
+    }
+    return out;
+}
+
 int env_int(const char* name, int dflt) { const char* v = std::getenv(name); return v && *v ? std::atoi(v) : dflt; }
 double env_double(const char* name, double dflt) { const char* v = std::getenv(name); return v && *v ? std::atof(v) : dflt; }
 
@@ -172,10 +194,8 @@ int flatten_scene(RtScene* s) {
     BlobWriter w{s->blob_host};
     rtd::SceneLayout& L = s->L;
     std::memset(&L, 0, sizeof(L));
-    L.box_a = w.add(s->bvh.box_a.data(), s->bvh.box_a.size() * 4);
-    L.box_b = w.add(s->bvh.box_b.data(), s->bvh.box_b.size() * 4);
-    L.box_c = w.add(s->bvh.box_c.data(), s->bvh.box_c.size() * 4);
-    L.child = w.add(s->bvh.child.data(), s->bvh.child.size() * 4);
+    const std::vector<float> nodes = octant_nodes(s->bvh);
+    L.nodes = w.add(nodes.data(), nodes.size() * 4);
     L.tri_a = w.add(tri_a.data(), tri_a.size() * 4);
     L.tri_e1 = w.add(tri_e1.data(), tri_e1.size() * 4);
     L.tri_e2 = w.add(tri_e2.data(), tri_e2.size() * 4);
@@ -190,18 +210,17 @@ int flatten_scene(RtScene* s) {
     L.lt_e2 = w.add(lt_e2.data(), lt_e2.size() * 4);
     L.lt_ng = w.add(lt_ng.data(), lt_ng.size() * 4);
     if (use_light_bvh) {
-        L.lbox_a = w.add(s->light_bvh.box_a.data(), s->light_bvh.box_a.size() * 4);
-        L.lbox_b = w.add(s->light_bvh.box_b.data(), s->light_bvh.box_b.size() * 4);
-        L.lbox_c = w.add(s->light_bvh.box_c.data(), s->light_bvh.box_c.size() * 4);
-        L.lchild = w.add(s->light_bvh.child.data(), s->light_bvh.child.size() * 4);
+        const std::vector<float> lnodes = octant_nodes(s->light_bvh);
+        L.lnodes = w.add(lnodes.data(), lnodes.size() * 4);
     }
     L.total_bytes = (uint32_t)s->blob_host.size();
     L.n_nodes = s->bvh.n_nodes; L.n_tris = n; L.n_mats = s->n_mats; L.n_lights = n_lights;
     L.n_lnodes = s->light_bvh.n_nodes; L.light_bvh = use_light_bvh ? 1 : 0;
 
-    const int need = std::max(s->bvh.depth, s->light_bvh.depth) + 2;
-    if (need <= 64) s->stack_entries = (uint32_t)std::max(8, (need + 3) / 4 * 4);
-    else return fail(RT_ERR_LIMIT, "BVH depth " + std::to_string(need - 2) + " exceeds the 62-entry traversal stack");
+    // entry 0 = RT_CUR_DONE, one marker per walk; the light-pdf walk runs on top of a ray's live stack (wavefront kernel)
+    const int need = s->bvh.depth + 3 + (use_light_bvh ? s->light_bvh.depth + 2 : 0);
+    if (need <= 96) s->stack_entries = (uint32_t)std::max(8, (need + 3) / 4 * 4);
+    else return fail(RT_ERR_LIMIT, "BVH depth " + std::to_string(s->bvh.depth) + " exceeds the traversal stack");
     const int smem_limit = env_int("RT_SMEM_SCENE_MAX_BYTES", 48 * 1024);
     s->use_smem = (int)L.total_bytes <= smem_limit;
     return RT_OK;

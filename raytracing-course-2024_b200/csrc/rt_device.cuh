@@ -53,12 +53,12 @@ RT_DEV float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); } 
 // kernels either read it through the read-only global path (ld.global.nc) or copy it to shared memory once per
 // CTA when it fits (practice7_4: ~12 KB) and read it with ld.shared -- same code, different Space.
 struct SceneLayout {
-    uint32_t box_a, box_b, box_c, child;         // finite-primitive BVH, child-pair nodes (host_scene.h)
+    uint32_t nodes;                              // finite-primitive BVH: octant-ordered child-pair nodes, RT_NODE_BYTES each (below)
     uint32_t tri_a, tri_e1, tri_e2;              // BVH-ordered triangles: a, b-a, c-a (w unused)
     uint32_t sh_n0, sh_dn1, sh_dn2, sh_ng;       // a_norm|material id, b_norm-a_norm|orig id, c_norm-a_norm, unit face normal
     uint32_t mat0, mat1;                         // base rgb|metallic, emission rgb|roughness
     uint32_t lt_a, lt_e1, lt_e2, lt_ng;          // light triangles (light-BVH order): a|1/area, e1, e2, unit normal
-    uint32_t lbox_a, lbox_b, lbox_c, lchild;     // light BVH (used when n_lights > RT_BRUTE_LIGHTS)
+    uint32_t lnodes;                             // light BVH, same node format (used when n_lights > RT_BRUTE_LIGHTS)
     uint32_t total_bytes;
     int32_t n_nodes, n_tris, n_mats, n_lights, n_lnodes;
     int32_t light_bvh;                           // 1: pdf walks the light BVH, 0: loops over all lights
@@ -84,22 +84,27 @@ struct GmemSpace {
     RT_DEV int2 ld2i(uint32_t off) const { return __ldg(reinterpret_cast<const int2*>(base + off)); }
 };
 
-// Per-thread traversal stack in shared memory, laid out [entry][thread]: bank = thread % 32 for every entry, so
-// pushes and pops are conflict-free however far the lanes' stack depths have diverged.
+// Per-thread traversal stack in shared memory, laid out [entry][thread]: bank = thread % 32 for every entry, so pushes
+// and pops are conflict-free however far the lanes' stack depths have diverged.  Entry 0 holds RT_CUR_DONE for good:
+// a pop never tests for an empty stack, the traversal is over when the popped reference is RT_CUR_DONE.
+#define RT_CUR_DONE ((int)0x80000000) /* never a node reference (>= 0) nor a leaf code (~code > INT_MIN) */
 struct SmemStack {
-    uint32_t addr;    // shared-window address of entry 0 of this thread
+    uint32_t top;     // shared-window address of the next free entry of this thread
     uint32_t stride;  // bytes between entries = 4 * blockDim.x
-    RT_DEV void store(int i, int v) const { asm volatile("st.shared.s32 [%0], %1;" ::"r"(addr + (uint32_t)i * stride), "r"(v)); }
-    RT_DEV int load(int i) const { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(addr + (uint32_t)i * stride)); return v; }
+    RT_DEV void init(uint32_t thread_entry0, uint32_t stride_bytes) {
+        stride = stride_bytes; top = thread_entry0 + stride_bytes;
+        asm volatile("st.shared.s32 [%0], %1;" ::"r"(thread_entry0), "r"(RT_CUR_DONE));
+    }
+    RT_DEV void reset(uint32_t thread_entry0) { top = thread_entry0 + stride; }
+    RT_DEV void push(int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(top), "r"(v)); top += stride; }
+    RT_DEV int pop() { int v; top -= stride; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(top)); return v; }
 };
 
 struct Counters { unsigned long long node_tests, tri_tests, light_tri_tests; };
 
 // ------------------------------------------------------------------------------------------------ intersection
-// Conservative slab test of the two child boxes of a pair node.  Same accept/prune rule as
-// get_aabb_intersection + bvh.rs:258-263: a box is entered iff the ray's [max(t_entry,0), t_exit] interval is
-// non-empty and t_entry <= best (prune iff best < t_entry while outside).  The reference perturbs the
-// direction by 1e-8 (geometry.rs:144-155); here zero components are replaced by +-1e-20 before inversion.
+// Reciprocal direction for the slab tests; zero components are replaced by +-1e-20 before inversion (the reference
+// adds 1e-8 to the direction instead, geometry.rs:144-155).
 RT_DEV float3 safe_inv_dir(float3 d) {
     const float tiny = 1e-20f;
     float x = fabsf(d.x) < tiny ? copysignf(tiny, d.x) : d.x;
@@ -107,15 +112,73 @@ RT_DEV float3 safe_inv_dir(float3 d) {
     float z = fabsf(d.z) < tiny ? copysignf(tiny, d.z) : d.z;
     return f3(fast_rcp(x), fast_rcp(y), fast_rcp(z));
 }
-RT_DEV bool slab(float lox, float hix, float loy, float hiy, float loz, float hiz, float3 inv, float3 od, float t_best, float& t_entry) {
-    float x0 = fmaf(lox, inv.x, -od.x), x1 = fmaf(hix, inv.x, -od.x);
-    float y0 = fmaf(loy, inv.y, -od.y), y1 = fmaf(hiy, inv.y, -od.y);
-    float z0 = fmaf(loz, inv.z, -od.z), z1 = fmaf(hiz, inv.z, -od.z);
-    float tmin = fmaxf(fmaxf(fminf(x0, x1), fminf(y0, y1)), fmaxf(fminf(z0, z1), 0.0f));
-    float tmax = fminf(fminf(fmaxf(x0, x1), fmaxf(y0, y1)), fminf(fmaxf(z0, z1), t_best));
-    t_entry = tmin;
-    // boxes are EPS-padded (1e-5, aabb.rs:53-65) and rounded outward: ~20 ulps of slack for the FP32 slab arithmetic
-    return tmin <= tmax;
+// Octant-ordered child-pair node (RT_NODE_BYTES = 112, 16-byte aligned).  A node keeps the boxes of BOTH children;
+// per axis it stores the four planes twice, once in each order, so that a ray picks its (near c0, near c1, far c0,
+// far c1) planes with ONE 16-byte load at an offset chosen by the sign of its direction -- no per-axis min/max:
+//   [ 0, 32) x: c0.min c1.min c0.max c1.max | c0.max c1.max c0.min c1.min
+//   [32, 64) y: same                          [64, 96) z: same
+//   [96,104) child references;  [104,112) padding
+// A child reference is >= 0 for an inner node (its BYTE offset inside the node array = index * 112, so a visit needs no
+// multiply) and < 0 for a leaf: ~((first_tri << 3) | (count - 1)).  The root is reference 0.
+#define RT_NODE_BYTES 112u
+struct RaySetup {
+    float3 inv, od;          // 1/d (zero components replaced, safe_inv_dir) and o/d
+    uint32_t ox, oy, oz;     // blob offsets of this ray's x / y / z plane quadruples of node 0
+};
+RT_DEV void ray_octant(RaySetup& r, uint32_t nodes) {
+    r.ox = nodes + ((__float_as_uint(r.inv.x) >> 27) & 16u);
+    r.oy = nodes + 32u + ((__float_as_uint(r.inv.y) >> 27) & 16u);
+    r.oz = nodes + 64u + ((__float_as_uint(r.inv.z) >> 27) & 16u);
+}
+RT_DEV RaySetup ray_setup(float3 o, float3 d, uint32_t nodes) {
+    RaySetup r;
+    r.inv = safe_inv_dir(d);
+    r.od = o * r.inv;
+    ray_octant(r, nodes);
+    return r;
+}
+RT_DEV float max3f(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+RT_DEV float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
+
+// One box-pair step of the near-child-first traversal (interesect_with_bvh_nearest_point, bvh.rs:231-297, iterative):
+// conservative slab test of the two child boxes of node `cur`, then descend into the nearer hit child (pushing the
+// other one), or pop.  Accept/prune rule of get_aabb_intersection + bvh.rs:258-263: a box is entered iff the ray's
+// [max(t_entry, 0), min(t_exit, best)] interval is non-empty.  Boxes are EPS-padded (1e-5, aabb.rs:53-65) and rounded
+// outward: ~20 ulps of slack for the FP32 arithmetic.  ORDERED = false: all-hits walk (children in storage order).
+// The child selection is written in PTX so that it stays in predicate registers (nvcc turns the bool algebra into
+// integer SEL / LOP3 / PRMT chains otherwise).
+template <class Space, bool ORDERED = true>
+RT_DEV void pair_step(const Space& sp, uint32_t nodes, const RaySetup& r, float t_best, int& cur, SmemStack& st) {
+    const uint32_t c = (uint32_t)cur;
+    const float4 X = sp.ld4(c + r.ox), Y = sp.ld4(c + r.oy), Z = sp.ld4(c + r.oz);
+    const int2 ch = sp.ld2i(c + (nodes + 96u));
+    const float nx0 = fmaf(X.x, r.inv.x, -r.od.x), nx1 = fmaf(X.y, r.inv.x, -r.od.x), fx0 = fmaf(X.z, r.inv.x, -r.od.x), fx1 = fmaf(X.w, r.inv.x, -r.od.x);
+    const float ny0 = fmaf(Y.x, r.inv.y, -r.od.y), ny1 = fmaf(Y.y, r.inv.y, -r.od.y), fy0 = fmaf(Y.z, r.inv.y, -r.od.y), fy1 = fmaf(Y.w, r.inv.y, -r.od.y);
+    const float nz0 = fmaf(Z.x, r.inv.z, -r.od.z), nz1 = fmaf(Z.y, r.inv.z, -r.od.z), fz0 = fmaf(Z.z, r.inv.z, -r.od.z), fz1 = fmaf(Z.w, r.inv.z, -r.od.z);
+    const float t0 = fmaxf(max3f(nx0, ny0, nz0), 0.0f), e0 = fminf(min3f(fx0, fy0, fz0), t_best);
+    const float t1 = fmaxf(max3f(nx1, ny1, nz1), 0.0f), e1 = fminf(min3f(fx1, fy1, fz1), t_best);
+    asm volatile(
+        "{\n\t"
+        ".reg .pred h0, h1, sf, both, any;\n\t"
+        ".reg .b32 first, second;\n\t"
+        "setp.le.f32 h0, %2, %4;\n\t"
+        "setp.le.f32 h1, %3, %5;\n\t"
+        "setp.lt.f32 sf, %3, %9;\n\t"                // second child first iff it is strictly nearer (ordered walks only) ...
+        "not.pred both, h0;\n\t"
+        "or.pred sf, sf, both;\n\t"                  // ... or the first child is not hit at all
+        "and.pred sf, sf, h1;\n\t"
+        "and.pred both, h0, h1;\n\t"
+        "or.pred any, h0, h1;\n\t"
+        "selp.b32 first, %7, %6, sf;\n\t"
+        "selp.b32 second, %6, %7, sf;\n\t"
+        "@both st.shared.b32 [%1], second;\n\t"
+        "@both add.u32 %1, %1, %8;\n\t"
+        "@any mov.b32 %0, first;\n\t"
+        "@!any sub.u32 %1, %1, %8;\n\t"
+        "@!any ld.shared.b32 %0, [%1];\n\t"
+        "}"
+        : "+r"(cur), "+r"(st.top)
+        : "f"(t0), "f"(t1), "f"(e0), "f"(e1), "r"(ch.x), "r"(ch.y), "r"(st.stride), "f"(ORDERED ? t0 : t1));
 }
 
 // Two-sided ray/triangle test with inclusive edges: u >= 0, v >= 0, u + v <= 1, t > 0 (geometry.rs:109-113).
@@ -146,33 +209,17 @@ struct Hit { float t, u, v; int tri; };
 // (rendering.rs:98) robust in FP32: a ray that LEAVES the side of the surface it started on cannot hit the
 // triangle it started from in exact arithmetic, so that triangle is skipped instead of relying on a 1e-5 gap.
 template <class Space, bool STATS>
-RT_DEV void trace_nearest(const Space& sp, const SceneLayout& L, const SmemStack& st, float3 o, float3 d, int skip_tri, Hit& hit, Counters& cnt) {
-    const float3 inv = safe_inv_dir(d);
-    const float3 od = o * inv;
+RT_DEV void trace_nearest(const Space& sp, const SceneLayout& L, SmemStack& st, float3 o, float3 d, int skip_tri, Hit& hit, Counters& cnt) {
+    const RaySetup r = ray_setup(o, d, L.nodes);
     hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
-    int cur = 0, sptr = 0;
+    st.push(RT_CUR_DONE);                        // marker: the walk may start on top of a live stack
+    int cur = 0;
     for (;;) {
-        bool done = false;
         while (cur >= 0) {
-            const uint32_t o16 = (uint32_t)cur * 16u;
-            const float4 A = sp.ld4(L.box_a + o16), B = sp.ld4(L.box_b + o16), C = sp.ld4(L.box_c + o16);
-            const int2 ch = sp.ld2i(L.child + (uint32_t)cur * 8u);
-            float t0, t1;
-            const bool h0 = slab(A.x, A.y, A.z, A.w, C.x, C.y, inv, od, hit.t, t0);
-            const bool h1 = slab(B.x, B.y, B.z, B.w, C.z, C.w, inv, od, hit.t, t1);
+            pair_step(sp, L.nodes, r, hit.t, cur, st);
             if (STATS) cnt.node_tests += 2;
-            if (h0 & h1) {
-                const bool swap = t1 < t0;
-                st.store(sptr++, swap ? ch.x : ch.y);
-                cur = swap ? ch.y : ch.x;
-            } else if (h0 | h1) {
-                cur = h0 ? ch.x : ch.y;
-            } else {
-                if (sptr == 0) { done = true; break; }
-                cur = st.load(--sptr);
-            }
         }
-        if (done) break;
+        if (cur == RT_CUR_DONE) break;
         const uint32_t code = (uint32_t)~cur;
         const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
         for (int i = first; i < first + n; ++i) {
@@ -183,8 +230,7 @@ RT_DEV void trace_nearest(const Space& sp, const SceneLayout& L, const SmemStack
             if (STATS) cnt.tri_tests += 1;
             if (ok && t < hit.t && i != skip_tri) { hit.t = t; hit.u = u; hit.v = v; hit.tri = i; }
         }
-        if (sptr == 0) break;
-        cur = st.load(--sptr);
+        cur = st.pop();
     }
 }
 
@@ -287,37 +333,26 @@ RT_DEV float light_tri_pdf(const Space& sp, const SceneLayout& L, int i, float3 
 // MultipleLightSamplingDistribution::pdf (distributions.rs:160-184): sum over ALL light triangles the ray
 // pierces, divided by the light count.  Few lights: plain loop (the reference's light BVH is a single leaf for
 // every shipped scene).  Many lights: all-hits walk of the light BVH = intersect_with_bvh_all_points
-// (bvh.rs:174-229): no pruning by distance, every intersected leaf triangle contributes.
+// (bvh.rs:174-229): no pruning by distance, every intersected leaf triangle contributes.  The walk pushes its own
+// RT_CUR_DONE marker first, so it can run on top of the traversal stack of a ray that is still in flight.
 template <class Space, bool STATS>
-RT_DEV float light_pdf(const Space& sp, const SceneLayout& L, const SmemStack& st, float3 point, float3 l, Counters& cnt) {
+RT_DEV float light_pdf(const Space& sp, const SceneLayout& L, SmemStack& st, float3 point, float3 l, Counters& cnt) {
     float sum = 0.0f;
     if (!L.light_bvh) {
         for (int i = 0; i < L.n_lights; ++i) sum += light_tri_pdf(sp, L, i, point, l);
         if (STATS) cnt.light_tri_tests += (unsigned long long)L.n_lights;
     } else {
-        const float3 inv = safe_inv_dir(l);
-        const float3 od = point * inv;
-        int cur = 0, sptr = 0;
+        const RaySetup r = ray_setup(point, l, L.lnodes);
+        st.push(RT_CUR_DONE);                    // marker: in the wavefront kernel the lane's own ray keeps its entries below
+        int cur = 0;
         for (;;) {
-            bool done = false;
-            while (cur >= 0) {
-                const uint32_t o16 = (uint32_t)cur * 16u;
-                const float4 A = sp.ld4(L.lbox_a + o16), B = sp.ld4(L.lbox_b + o16), C = sp.ld4(L.lbox_c + o16);
-                const int2 ch = sp.ld2i(L.lchild + (uint32_t)cur * 8u);
-                float t0, t1;
-                const bool h0 = slab(A.x, A.y, A.z, A.w, C.x, C.y, inv, od, RT_INF_F, t0);
-                const bool h1 = slab(B.x, B.y, B.z, B.w, C.z, C.w, inv, od, RT_INF_F, t1);
-                if (h0 & h1) { st.store(sptr++, ch.y); cur = ch.x; }
-                else if (h0 | h1) cur = h0 ? ch.x : ch.y;
-                else { if (sptr == 0) { done = true; break; } cur = st.load(--sptr); }
-            }
-            if (done) break;
+            while (cur >= 0) pair_step<Space, false>(sp, L.lnodes, r, RT_INF_F, cur, st);
+            if (cur == RT_CUR_DONE) break;
             const uint32_t code = (uint32_t)~cur;
             const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
             for (int i = first; i < first + n; ++i) sum += light_tri_pdf(sp, L, i, point, l);
             if (STATS) cnt.light_tri_tests += (unsigned long long)n;
-            if (sptr == 0) break;
-            cur = st.load(--sptr);
+            cur = st.pop();
         }
     }
     return sum / (float)L.n_lights;

@@ -63,7 +63,7 @@ RT_DEV void camera_ray(const Camera& c, int W, int H, int x, int y, float xi1, f
 // (distributions.rs:188-192) followed by MixDistribution::pdf (:194-201).  Returns the mixture pdf; `terms` are
 // the per-direction quantities for the BRDF of the accepted direction.
 template <class Space, bool STATS>
-RT_DEV float mix_sample_and_pdf(const Space& sp, const SceneLayout& L, const SmemStack& st, int n_comp, float3 P, float3 n, float3 v,
+RT_DEV float mix_sample_and_pdf(const Space& sp, const SceneLayout& L, SmemStack& st, int n_comp, float3 P, float3 n, float3 v,
                                 float nv, float alpha, float alpha2, float g1v, uint4 rnd, float3& l, DirTerms& terms, Counters& cnt) {
     const uint32_t comp = __umulhi(rnd.x, (uint32_t)n_comp);           // gen_range(0..len)
     const float u1 = u01(rnd.y), u2 = u01(rnd.z);
@@ -96,7 +96,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS) render_kernel(const R
     }
     const Space sp = SpaceMaker<Space>::make(a.blob, smem_base + stack_bytes);
     const SceneLayout& L = a.L;
-    SmemStack st; st.addr = smem_base + threadIdx.x * 4u; st.stride = blockDim.x * 4u;
+    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u);
     const unsigned lane = threadIdx.x & 31u;
     const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
     const float3 bg = f3(a.bg[0], a.bg[1], a.bg[2]);
@@ -353,7 +353,7 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const char* blob, const
                                                          const double* __restrict__ rays, long long n, int32_t* __restrict__ tri_id, double* __restrict__ t_out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    SmemStack st; st.addr = smem_base + threadIdx.x * 4u; st.stride = blockDim.x * 4u;
+    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u);
     GmemSpace sp; sp.base = blob;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -365,24 +365,12 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const char* blob, const
         trace_nearest<GmemSpace, false>(sp, L, st, o, d, -1, hit, cnt);
         best = hit.tri; best_t = hit.tri >= 0 ? (double)hit.t : best_t;
     } else {
-        const float3 inv = safe_inv_dir(d);
-        const float3 odf = o * inv;
+        const RaySetup r = ray_setup(o, d, L.nodes);
         float best_tf = RT_INF_F;
-        int cur = 0, sptr = 0;
+        int cur = 0;
         for (;;) {
-            bool done = false;
-            while (cur >= 0) {
-                const uint32_t o16 = (uint32_t)cur * 16u;
-                const float4 A = sp.ld4(L.box_a + o16), B = sp.ld4(L.box_b + o16), C = sp.ld4(L.box_c + o16);
-                const int2 ch = sp.ld2i(L.child + (uint32_t)cur * 8u);
-                float t0, t1;
-                const bool h0 = slab(A.x, A.y, A.z, A.w, C.x, C.y, inv, odf, best_tf, t0);
-                const bool h1 = slab(B.x, B.y, B.z, B.w, C.z, C.w, inv, odf, best_tf, t1);
-                if (h0 & h1) { const bool swap = t1 < t0; st.store(sptr++, swap ? ch.x : ch.y); cur = swap ? ch.y : ch.x; }
-                else if (h0 | h1) cur = h0 ? ch.x : ch.y;
-                else { if (sptr == 0) { done = true; break; } cur = st.load(--sptr); }
-            }
-            if (done) break;
+            while (cur >= 0) pair_step(sp, L.nodes, r, best_tf, cur, st);
+            if (cur == RT_CUR_DONE) break;
             const uint32_t code = (uint32_t)~cur;
             const int first = (int)(code >> 3), cntl = (int)(code & 7u) + 1;
             for (int k = first; k < first + cntl; ++k) {
@@ -392,8 +380,7 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const char* blob, const
                     best_tf = __double2float_ru(t) * 1.000001f;   // prune bound rounded up: boxes stay conservative
                 }
             }
-            if (sptr == 0) break;
-            cur = st.load(--sptr);
+            cur = st.pop();
         }
     }
     tri_id[i] = best >= 0 ? __float_as_int(sp.ld4(L.sh_dn1 + (uint32_t)best * 16u).w) : -1;
@@ -452,7 +439,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const char* blob, const Scene
                                                    const float* __restrict__ in, long long n, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    SmemStack st; st.addr = smem_base + threadIdx.x * 4u; st.stride = blockDim.x * 4u;
+    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u);
     GmemSpace sp; sp.base = blob;
     Counters cnt; cnt.node_tests = 0; cnt.tri_tests = 0; cnt.light_tri_tests = 0;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;

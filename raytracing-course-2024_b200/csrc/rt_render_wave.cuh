@@ -21,9 +21,17 @@
 #pragma once
 
 #define RT_POOL_SLOTS 64
-enum { F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_SKIP, F_TRI, F_U, F_V, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ, F_PIX, F_S, F_SSTOP, F_CHUNK, F_META, F_TQ, F_SQ, NF };
+// Slot fields (words, SoA [field][slot]).  A slot is read by the shade round and by the lane that traces its ray, never
+// by both at once, so hand-over fields share storage:
+//   shade -> trace: O (ray origin), D (direction), IV (safe reciprocal direction), F_TRI = triangle to skip (or -1)
+//   trace -> shade: F_TRI = nearest triangle (or -1), (F_U, F_V) = its barycentrics; D is still the ray direction
+// While a ray is in flight its lane keeps only (1/d, o/d, octant offsets, best t, best triangle, node, stack pointer) in
+// registers -- they must survive the shade rounds the warp runs for OTHER slots -- and re-reads O, D and the skip
+// triangle from the slot whenever it reaches a leaf.
+enum { F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_IX, F_IY, F_IZ, F_TRI, F_U, F_V, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ, F_PIX, F_S, F_CHUNK, F_META, NF };
+#define RT_POOL_QUEUE_BYTES (2u * RT_POOL_SLOTS)                       /* TQ and SQ: one byte per entry */
+#define RT_POOL_WARP_BYTES (RT_POOL_SLOTS * NF * 4u + RT_POOL_QUEUE_BYTES)
 enum { ST_NEED_ITEM = 0, ST_NEED_PATH = 1, ST_GEN = 2, ST_TRACE = 3, ST_RETRY = 4, ST_EXHAUSTED = 5, ST_NONE = 6 };
-#define RT_CUR_DONE ((int)0x80000000)
 
 struct Pool {
     uint32_t base;
@@ -34,6 +42,10 @@ struct Pool {
     RT_DEV void sti(int f, int s, int v) const { asm volatile("st.shared.s32 [%0], %1;" ::"r"(at(f, s)), "r"(v)); }
     RT_DEV float3 ld3(int f, int s) const { return f3(ldf(f, s), ldf(f + 1, s), ldf(f + 2, s)); }
     RT_DEV void st3(int f, int s, float3 v) const { stf(f, s, v.x); stf(f + 1, s, v.y); stf(f + 2, s, v.z); }
+    // queues: q = 0 (TQ) or 1 (SQ), pos in [0, RT_POOL_SLOTS)
+    RT_DEV uint32_t qat(int q, int pos) const { return base + RT_POOL_SLOTS * NF * 4u + (uint32_t)(q * RT_POOL_SLOTS + pos); }
+    RT_DEV int qld(int q, int pos) const { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(qat(q, pos))); return v; }
+    RT_DEV void qst(int q, int pos, int v) const { asm volatile("st.shared.u8 [%0], %1;" ::"r"(qat(q, pos)), "r"(v)); }
 };
 // meta word of a slot: state (3 bits) | segments left (8) | attempts made at this vertex (7) | Philox call counter (14)
 RT_DEV uint32_t pack_meta(int state, int depth, int attempt, uint32_t call) { return (uint32_t)state | ((uint32_t)depth << 3) | ((uint32_t)attempt << 11) | (call << 18); }
@@ -55,11 +67,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
     }
     const Space sp = SpaceMaker<Space>::make(a.blob, smem_base + stack_bytes);
     const SceneLayout& L = a.L;
-    SmemStack st; st.addr = smem_base + threadIdx.x * 4u; st.stride = blockDim.x * 4u;
+    SmemStack st; st.init(smem_base + threadIdx.x * 4u, BLOCK * 4u);
+    const uint32_t stack0 = smem_base + threadIdx.x * 4u;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
     const unsigned FULL = 0xffffffffu;
-    Pool pool; pool.base = smem_base + stack_bytes + blob_bytes + warp * (uint32_t)(P * NF * 4);
+    Pool pool; pool.base = smem_base + stack_bytes + blob_bytes + warp * RT_POOL_WARP_BYTES;
     const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
     const float3 bg = f3(a.bg[0], a.bg[1], a.bg[2]);
     const bool bg_nonzero = (a.bg[0] != 0.f) | (a.bg[1] != 0.f) | (a.bg[2] != 0.f);
@@ -71,13 +84,34 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
 
     // ring queues: positions in [0, P), counts separate (all warp-uniform)
     int tq_head = 0, tq_n = 0, sq_head = 0, sq_n = P;
-    for (int s = (int)lane; s < P; s += 32) { pool.sti(F_META, s, (int)pack_meta(ST_NEED_ITEM, 0, 0, 0u)); pool.sti(F_SQ, s, s); }
+    for (int s = (int)lane; s < P; s += 32) { pool.sti(F_META, s, (int)pack_meta(ST_NEED_ITEM, 0, 0, 0u)); pool.qst(1, s, s); }
     __syncwarp();
 
-    // traversal state of this lane's in-flight ray
-    int slot = -1, cur = RT_CUR_DONE, sptr = 0, skip_tri = -1;
-    float3 o = f3(0.f, 0.f, 0.f), d = f3(0.f, 0.f, 1.f), inv = f3(1.f, 1.f, 1.f), od = f3(0.f, 0.f, 0.f);
-    Hit hit; hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
+    // traversal state of this lane's in-flight ray (the stack pointer lives in `st`)
+    int slot = -1, cur = RT_CUR_DONE, hit_tri = -1;
+    float t_best = RT_INF_F;
+    RaySetup rs; rs.inv = f3(1.f, 1.f, 1.f); rs.od = f3(0.f, 0.f, 0.f); rs.ox = 0u; rs.oy = 32u; rs.oz = 64u;
+
+    // box-pair step and leaf step of the lane's ray (callers predicate them)
+    auto node_step = [&]() {
+        pair_step(sp, L.nodes, rs, t_best, cur, st);
+        if (STATS) cnt.node_tests += 2;
+    };
+    auto leaf_step = [&]() {
+        const uint32_t code = (uint32_t)~cur;
+        const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
+        const float3 o = pool.ld3(F_OX, slot), d = pool.ld3(F_DX, slot);
+        const int skip_tri = pool.ldi(F_TRI, slot);
+        for (int i = first; i < first + n; ++i) {
+            const uint32_t o16 = (uint32_t)i * 16u;
+            const float4 ta = sp.ld4(L.tri_a + o16), e1 = sp.ld4(L.tri_e1 + o16), e2 = sp.ld4(L.tri_e2 + o16);
+            float t, u, v;
+            const bool ok = tri_test(o, d, f3(ta), f3(e1), f3(e2), t, u, v);
+            if (STATS) cnt.tri_tests += 1;
+            if (ok && t < t_best && i != skip_tri) { t_best = t; hit_tri = i; pool.stf(F_U, slot, u); pool.stf(F_V, slot, v); }
+        }
+        cur = st.pop();
+    };
 
     for (;;) {
         // ---------------------------------------------------------------------------------- retire finished rays, refill from TQ
@@ -86,8 +120,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
             const unsigned fin = __ballot_sync(FULL, finished);
             if (fin != 0u) {
                 if (finished) {
-                    pool.sti(F_TRI, slot, hit.tri); pool.stf(F_U, slot, hit.u); pool.stf(F_V, slot, hit.v);
-                    pool.sti(F_SQ, (sq_head + sq_n + __popc(fin & lt_mask)) & (P - 1), slot);
+                    pool.sti(F_TRI, slot, hit_tri);
+                    pool.qst(1, (sq_head + sq_n + __popc(fin & lt_mask)) & (P - 1), slot);
                     slot = -1;
                 }
                 sq_n += __popc(fin);
@@ -97,12 +131,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
             if (n_idle > 0 && tq_n > 0) {
                 const int rank = __popc(idle & lt_mask);
                 if (slot < 0 && rank < tq_n) {
-                    slot = pool.ldi(F_TQ, (tq_head + rank) & (P - 1));
-                    o = pool.ld3(F_OX, slot); d = pool.ld3(F_DX, slot);
-                    skip_tri = pool.ldi(F_SKIP, slot);
-                    inv = safe_inv_dir(d); od = o * inv;
-                    hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
-                    cur = 0; sptr = 0;
+                    slot = pool.qld(0, (tq_head + rank) & (P - 1));
+                    rs.inv = pool.ld3(F_IX, slot); rs.od = pool.ld3(F_OX, slot) * rs.inv; ray_octant(rs, L.nodes);
+                    t_best = RT_INF_F; hit_tri = -1;
+                    cur = 0; st.reset(stack0);
                     if (STATS) ++c_segments;
                 }
                 const int took = min(n_idle, tq_n);
@@ -116,7 +148,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 int s = 0, state = ST_NONE;
                 uint32_t meta = 0;
                 if ((int)lane < n_take) {
-                    s = pool.ldi(F_SQ, (sq_head + (int)lane) & (P - 1));
+                    s = pool.qld(1, (sq_head + (int)lane) & (P - 1));
                     meta = (uint32_t)pool.ldi(F_META, s);
                     state = (int)(meta & 7u);
                 }
@@ -169,8 +201,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                                 T = T * f * (terms.nl * fast_rcp(pdf));          // :122
                                 if (!finite3(T)) { if (STATS) ++c_nonfinite; end_path = true; }
                                 else {
-                                    pool.st3(F_OX, s, Pt); pool.st3(F_DX, s, l); pool.st3(F_TX, s, T);
-                                    pool.sti(F_SKIP, s, terms.nl > 0.0f ? tri : -1);
+                                    pool.st3(F_OX, s, Pt); pool.st3(F_DX, s, l); pool.st3(F_IX, s, safe_inv_dir(l)); pool.st3(F_TX, s, T);
+                                    pool.sti(F_TRI, s, terms.nl > 0.0f ? tri : -1);
                                     attempt = 0; state = ST_TRACE;
                                 }
                             } else if (attempt >= a.max_attempts || attempt >= 127) {
@@ -185,10 +217,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                     meta = pack_meta(state, depth, attempt, call);
                 }
                 if (state == ST_NEED_PATH) {                                     // next sample of this item, or store the item
-                    const int s_next = pool.ldi(F_S, s) + 1, s_stop = pool.ldi(F_SSTOP, s);
+                    const int chunk = pool.ldi(F_CHUNK, s);
+                    const int s_next = pool.ldi(F_S, s) + 1, s_stop = min(a.s_begin + (chunk + 1) * a.chunk_size, a.s_end);
                     if (s_next < s_stop) { pool.sti(F_S, s, s_next); state = ST_GEN; }
                     else {
-                        const int chunk = pool.ldi(F_CHUNK, s);
                         const uint32_t pix = (uint32_t)pool.ldi(F_PIX, s);
                         const float3 acc = pool.ld3(F_AX, s);
                         const float n_done = (float)(s_stop - (a.s_begin + chunk * a.chunk_size));
@@ -218,7 +250,6 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                                 pool.sti(F_PIX, s, (int)((uint32_t)py * (uint32_t)a.W + (uint32_t)px));
                                 pool.sti(F_CHUNK, s, (int)chunk);
                                 pool.sti(F_S, s, s0);
-                                pool.sti(F_SSTOP, s, min(s0 + a.chunk_size, a.s_end));
                                 pool.st3(F_AX, s, f3(0.f, 0.f, 0.f));
                                 state = ST_GEN;
                             }
@@ -232,8 +263,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                     const uint4 rr = philox4x32_10(make_uint4(pix, (uint32_t)s_this, 0u, RT_PHILOX_TAG), key);
                     float3 co, cd;
                     camera_ray(a.cam, a.W, a.H, px, py, u01(rr.x), u01(rr.y), co, cd);
-                    pool.st3(F_OX, s, co); pool.st3(F_DX, s, cd); pool.st3(F_TX, s, f3(1.f, 1.f, 1.f));
-                    pool.sti(F_SKIP, s, -1);
+                    pool.st3(F_OX, s, co); pool.st3(F_DX, s, cd); pool.st3(F_IX, s, safe_inv_dir(cd)); pool.st3(F_TX, s, f3(1.f, 1.f, 1.f));
+                    pool.sti(F_TRI, s, -1);
                     state = ST_TRACE;
                     meta = pack_meta(state, a.ray_depth > 255 ? 255 : a.ray_depth, 0, 1u);
                     if (STATS) ++c_samples;
@@ -242,10 +273,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 }
                 if (state != ST_NONE) pool.sti(F_META, s, (int)meta);
                 const unsigned to_tq = __ballot_sync(FULL, state == ST_TRACE);
-                if (state == ST_TRACE) pool.sti(F_TQ, (tq_head + tq_n + __popc(to_tq & lt_mask)) & (P - 1), s);
+                if (state == ST_TRACE) pool.qst(0, (tq_head + tq_n + __popc(to_tq & lt_mask)) & (P - 1), s);
                 tq_n += __popc(to_tq);
                 const unsigned to_sq = __ballot_sync(FULL, state == ST_RETRY);   // rejected attempt: retry in a later round
-                if (state == ST_RETRY) pool.sti(F_SQ, (sq_head + sq_n + __popc(to_sq & lt_mask)) & (P - 1), s);
+                if (state == ST_RETRY) pool.qst(1, (sq_head + sq_n + __popc(to_sq & lt_mask)) & (P - 1), s);
                 sq_n += __popc(to_sq);
                 __syncwarp();
                 continue;
@@ -256,85 +287,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
         // ---------------------------------------------------------------------------------- trace burst
         if (MODE == 0) {
             for (;;) {
-                while (cur >= 0) {
-                    const uint32_t o16 = (uint32_t)cur * 16u;
-                    const float4 A = sp.ld4(L.box_a + o16), B = sp.ld4(L.box_b + o16), C = sp.ld4(L.box_c + o16);
-                    const int2 ch = sp.ld2i(L.child + (uint32_t)cur * 8u);
-                    float t0, t1;
-                    const bool h0 = slab(A.x, A.y, A.z, A.w, C.x, C.y, inv, od, hit.t, t0);
-                    const bool h1 = slab(B.x, B.y, B.z, B.w, C.z, C.w, inv, od, hit.t, t1);
-                    if (STATS) cnt.node_tests += 2;
-                    if (h0 & h1) {
-                        const bool swap = t1 < t0;
-                        st.store(sptr++, swap ? ch.x : ch.y);
-                        cur = swap ? ch.y : ch.x;
-                    } else if (h0 | h1) {
-                        cur = h0 ? ch.x : ch.y;
-                    } else {
-                        cur = sptr == 0 ? RT_CUR_DONE : st.load(--sptr);
-                    }
-                }
-                if (cur != RT_CUR_DONE) {
-                    const uint32_t code = (uint32_t)~cur;
-                    const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
-                    for (int i = first; i < first + n; ++i) {
-                        const uint32_t o16 = (uint32_t)i * 16u;
-                        const float4 ta = sp.ld4(L.tri_a + o16), e1 = sp.ld4(L.tri_e1 + o16), e2 = sp.ld4(L.tri_e2 + o16);
-                        float t, u, v;
-                        const bool ok = tri_test(o, d, f3(ta), f3(e1), f3(e2), t, u, v);
-                        if (STATS) cnt.tri_tests += 1;
-                        if (ok && t < hit.t && i != skip_tri) { hit.t = t; hit.u = u; hit.v = v; hit.tri = i; }
-                    }
-                    cur = sptr == 0 ? RT_CUR_DONE : st.load(--sptr);
-                }
+                while (cur >= 0) node_step();
+                if (cur != RT_CUR_DONE) leaf_step();
                 if (__popc(__ballot_sync(FULL, cur == RT_CUR_DONE)) >= burst_exit) break;
             }
         } else {
-            // phased burst: box-pair steps run while at least `node_min` lanes want one; otherwise the lanes that sit on a
-            // leaf test its triangles; the minority keeps its state and waits for its phase.
-            for (bool progressed = false;; progressed = true) {
-                const int nn = __popc(__ballot_sync(FULL, cur >= 0));
-                bool node_step = nn >= node_min;
-                if (!node_step) {
-                    const bool at_leaf = cur < 0 && cur != RT_CUR_DONE;
-                    if (__ballot_sync(FULL, at_leaf) != 0u) {
-                        if (at_leaf) {
-                            const uint32_t code = (uint32_t)~cur;
-                            const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
-                            for (int i = first; i < first + n; ++i) {
-                                const uint32_t o16 = (uint32_t)i * 16u;
-                                const float4 ta = sp.ld4(L.tri_a + o16), e1 = sp.ld4(L.tri_e1 + o16), e2 = sp.ld4(L.tri_e2 + o16);
-                                float t, u, v;
-                                const bool ok = tri_test(o, d, f3(ta), f3(e1), f3(e2), t, u, v);
-                                if (STATS) cnt.tri_tests += 1;
-                                if (ok && t < hit.t && i != skip_tri) { hit.t = t; hit.u = u; hit.v = v; hit.tri = i; }
-                            }
-                            cur = sptr == 0 ? RT_CUR_DONE : st.load(--sptr);
-                        }
-                        if (__popc(__ballot_sync(FULL, cur == RT_CUR_DONE)) >= burst_exit) break;
-                        continue;
-                    }
-                    if (nn == 0 || (progressed && 32 - nn >= burst_exit)) break;  // only box-pair lanes and finished lanes are left
-                    node_step = true;
+            // phased burst: box-pair steps run while at least `nmin` lanes want one; otherwise the lanes that sit on a leaf
+            // test its triangles; the minority keeps its state and waits for its phase.  nmin <= live lanes, so a burst
+            // always advances some ray; it ends when `burst_exit` lanes are finished (or idle).
+            const int nmin = min(node_min, __popc(__ballot_sync(FULL, slot >= 0)));
+            for (;;) {
+                for (;;) {
+                    if (__popc(__ballot_sync(FULL, cur >= 0)) < nmin) break;
+                    if (cur >= 0) node_step();
                 }
-                if (cur >= 0) {
-                    const uint32_t o16 = (uint32_t)cur * 16u;
-                    const float4 A = sp.ld4(L.box_a + o16), B = sp.ld4(L.box_b + o16), C = sp.ld4(L.box_c + o16);
-                    const int2 ch = sp.ld2i(L.child + (uint32_t)cur * 8u);
-                    float t0, t1;
-                    const bool h0 = slab(A.x, A.y, A.z, A.w, C.x, C.y, inv, od, hit.t, t0);
-                    const bool h1 = slab(B.x, B.y, B.z, B.w, C.z, C.w, inv, od, hit.t, t1);
-                    if (STATS) cnt.node_tests += 2;
-                    if (h0 & h1) {
-                        const bool swap = t1 < t0;
-                        st.store(sptr++, swap ? ch.x : ch.y);
-                        cur = swap ? ch.y : ch.x;
-                    } else if (h0 | h1) {
-                        cur = h0 ? ch.x : ch.y;
-                    } else {
-                        cur = sptr == 0 ? RT_CUR_DONE : st.load(--sptr);
-                    }
-                }
+                const bool at_leaf = cur < 0 && cur != RT_CUR_DONE;
+                if (__ballot_sync(FULL, at_leaf) == 0u) break;                   // fewer than nmin box-pair lanes, the rest finished
+                if (at_leaf) leaf_step();
+                if (__popc(__ballot_sync(FULL, cur == RT_CUR_DONE)) >= burst_exit) break;
             }
         }
     }
@@ -349,7 +319,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
 
 template <class Space, bool STATS, int MODE, int BLOCK, int MINB>
 static cudaError_t launch_wave_t(const RenderArgs& a, int device_sms, cudaStream_t stream, KernelInfo* info, bool launch, int* lanes) {
-    const uint32_t smem = a.stack_entries * BLOCK * 4u + (IsSmem<Space>::value ? a.L.total_bytes : 0u) + (BLOCK / 32) * (uint32_t)(RT_POOL_SLOTS * NF * 4);
+    const uint32_t smem = a.stack_entries * BLOCK * 4u + (IsSmem<Space>::value ? a.L.total_bytes : 0u) + (BLOCK / 32) * RT_POOL_WARP_BYTES;
     auto kern = render_wave_kernel<Space, STATS, MODE, BLOCK, MINB>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
