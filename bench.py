@@ -147,6 +147,14 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def kernel_name(st):
+    space = "SmemSpace" if st["scene_in_shared_memory"] else "GmemSpace"
+    if st["kernel"] == 1:
+        return f"render_kernel<{space},false> (v1 per-lane megakernel)"
+    mode = {2: "0 (while-while bursts)", 3: "1 (phased bursts)"}.get(st["kernel"], "?")
+    return f"render_wave_kernel<{space},false,MODE={mode},BLOCK={st['block_threads']},MINB={st['blocks_per_sm']}> (v3 warp-local wavefront)"
+
+
 # ------------------------------------------------------------------------------------------------ B200 arm
 def main():
     args = parse()
@@ -221,6 +229,7 @@ def main():
         sw, sh = max(64, W // 8), max(36, H // 8)
         scene.set_frame(sw, sh, 64)
         _, st = scene.render_linear(seed=args.seed, collect_stats=True)
+        _, kcfg = scene.render(seed=args.seed, kernel_variant=args.variant)                 # the timed build's launch configuration
         scene.set_frame(W, H, S)
         n = st["samples"]
         counts = {k: st[k] / n for k in ("segments", "vertices", "attempts", "node_tests", "tri_tests", "light_tri_tests")}
@@ -294,7 +303,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "scene file scenes/practice7_4.gltf (fixed input, 92 triangles); no synthetic tensors",
             "config": {"workload": f"{args.scene} {W}x{H} {S} spp ray_depth 6, sample-sharded over {world} GPU(s), Philox seed {args.seed}",
-                       "l2_note": "inputs are a 13 KB scene staged in shared memory; each step rewrites the %.0f MB accumulator (> L2 is not needed: nothing is re-read across steps)" % (hbm_bytes / 3 / 1e6),
+                       "l2_note": "inputs are a 17 KB scene staged in shared memory; each step rewrites the %.0f MB accumulator (> L2 is not needed: nothing is re-read across steps)" % (hbm_bytes / 3 / 1e6),
                        "scene_in_shared_memory": bool(info["scene_in_shared_memory"]), "bvh_nodes": info["n_nodes"], "kernel_variant": args.variant},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(info["device_bytes"]) * world, "d2h_bytes_per_step": W * H * 3,
                     "steps": e2e_n, "ms_per_step": e2e_ms / e2e_n},
@@ -302,7 +311,8 @@ def main():
             "clocks": clk,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None,
                          "traffic": None, "peak_source": "FFMA micro-benchmark measured in this process (MEASURED_PEAKS.json has no FP32 entry)",
-                         "kernel": "render_kernel<SmemSpace,false>", "kernel_ms": kern_ms, "flop_per_sample": flop_per_sample, "per_sample": counts,
+                         "kernel": kernel_name(kcfg), "launch": {k: kcfg[k] for k in ("block_threads", "blocks_per_sm", "grid_blocks", "regs_per_thread", "smem_bytes_per_block")},
+                         "kernel_ms": kern_ms, "flop_per_sample": flop_per_sample, "per_sample": counts,
                          "flop_constants": {"node": C_NODE, "tri": C_TRI, "attempt": C_ATTEMPT, "shade": C_SHADE},
                          "hbm_algorithmic_bytes": hbm_bytes, "hbm_achieved_gbs": hbm_bytes / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
                          "hbm_frac": (hbm_bytes / (kern_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,

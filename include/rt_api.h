@@ -75,7 +75,7 @@ typedef struct RtRenderParams {
     int32_t max_attempts;             /* cap of the rejection loop rendering.rs:102-110 (0 = default 64)  */
     int32_t collect_stats;            /* 1: run the instrumented kernel and fill the work counters         */
     int32_t kernel_variant;           /* 0 = auto; else 10*kernel + placement (benchmarks / A-B tests):
-                                         kernel 1 = per-lane megakernel, 2 / 3 = warp-local wavefront with 64 / 96 slots per warp;
+                                         kernel 1 = per-lane megakernel, 2 / 3 = warp-local wavefront with while-while / phased trace bursts;
                                          placement 1 = scene in global memory, 2 = scene in shared memory   */
     int32_t reserved[3];
 } RtRenderParams;
@@ -93,6 +93,9 @@ typedef struct RtStats {
     uint64_t kernel_launches;         /* CUDA kernels launched by this call                                */
     double   kernel_ms;               /* device time of the render kernels (CUDA events)                   */
     double   total_ms;                /* device time of the whole call incl. copies (CUDA events)          */
+    int32_t  kernel;                  /* render kernel that ran: 1 = per-lane megakernel, 2 / 3 = warp-local wavefront (while-while / phased bursts) */
+    int32_t  block_threads, blocks_per_sm, grid_blocks, regs_per_thread, smem_bytes_per_block;   /* its launch configuration */
+    int32_t  scene_in_shared_memory;  /* 1: the scene blob was staged in shared memory by every block      */
 } RtStats;
 
 /* ---- error reporting ------------------------------------------------------------------------------------ */

@@ -300,20 +300,20 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     const uint32_t tiles_y = (uint32_t)((h.height + 3) / 4);
     a.n_pix_items = a.tiles_x * tiles_y * 32u;
     a.stack_entries = s->stack_entries;
-    a.node_min = std::min(32, std::max(1, env_int("RT_NODE_MIN", 16)));
-    a.burst_exit = std::min(32, std::max(1, env_int("RT_BURST_EXIT", 8)));
+    a.node_min = std::min(32, std::max(1, env_int("RT_NODE_MIN", 8)));
+    a.burst_exit = std::min(32, std::max(1, env_int("RT_BURST_EXIT", 12)));
     a.seed_lo = (uint32_t)(p->seed & 0xffffffffu); a.seed_hi = (uint32_t)(p->seed >> 32);
     plan->stats = p->collect_stats != 0;
-    // kernel_variant = 10*kernel + scene placement: kernel 0 auto (= 2), 1 = v1 per-lane megakernel, 2 / 3 = v3 warp-local
+    // kernel_variant = 10*kernel + scene placement: kernel 0 auto (= 3), 1 = v1 per-lane megakernel, 2 / 3 = v3 warp-local
     // wavefront with while-while / phased trace bursts; placement 0 auto, 1 global memory, 2 shared memory
     plan->use_smem = s->use_smem;
     const int placement = p->kernel_variant % 10, kern = p->kernel_variant / 10;
     if (placement == 1) plan->use_smem = false;
     if (placement == 2) plan->use_smem = true;
-    plan->variant = kern == 0 ? env_int("RT_KERNEL", 2) : kern;
+    plan->variant = kern == 0 ? env_int("RT_KERNEL", 3) : kern;
     if (plan->variant < 1 || plan->variant > 3) return fail(RT_ERR_INVALID, "kernel_variant: unknown kernel");
 
-    plan->cfg = env_int("RT_WAVE_CFG", 0);
+    plan->cfg = env_int("RT_WAVE_CFG", 2);
     // sample chunks: enough (pixel, chunk) items to keep every resident lane busy ~4 times over
     int lanes = 0;
     CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
@@ -339,10 +339,12 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     return RT_OK;
 }
 
-int collect_stats(RtScene* s, const RenderPlan& plan, RtStats* st, int launches, cudaStream_t stream) {
+int collect_stats(RtScene* s, const RenderPlan& plan, const rtd::KernelInfo& ki, RtStats* st, int launches, cudaStream_t stream) {
     if (!st) return RT_OK;
     std::memset(st, 0, sizeof(*st));
     st->kernel_launches = (uint64_t)launches;
+    st->kernel = plan.variant; st->block_threads = ki.block; st->blocks_per_sm = ki.blocks_per_sm; st->grid_blocks = ki.grid;
+    st->regs_per_thread = ki.regs; st->smem_bytes_per_block = ki.smem_bytes; st->scene_in_shared_memory = plan.use_smem ? 1 : 0;
     if (plan.stats) {
         unsigned long long v[rtd::RT_N_STATS];
         CUDA_TRY(cudaMemcpyAsync(v, s->stats_dev, sizeof(v), cudaMemcpyDeviceToHost, stream));
@@ -476,7 +478,7 @@ int rt_render(RtScene* s, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st
     CUDA_TRY(cudaMemcpyAsync(rgb_out, s->rgb_dev, n_pix * 3, cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaEventRecord(s->ev[3], stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    if ((rc = collect_stats(s, plan, st, 3, stream)) != RT_OK) return rc;
+    if ((rc = collect_stats(s, plan, ki, st, 3, stream)) != RT_OK) return rc;
     if (st) {
         float k = 0, t = 0;
         cudaEventElapsedTime(&k, s->ev[1], s->ev[2]); cudaEventElapsedTime(&t, s->ev[0], s->ev[3]);
@@ -503,7 +505,7 @@ int rt_render_linear(RtScene* s, const RtRenderParams* p, float* out, RtStats* s
     CUDA_TRY(cudaMemcpyAsync(out, s->lin_dev, n_pix * 3 * sizeof(float), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaEventRecord(s->ev[3], stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
-    if ((rc = collect_stats(s, plan, st, 3, stream)) != RT_OK) return rc;
+    if ((rc = collect_stats(s, plan, ki, st, 3, stream)) != RT_OK) return rc;
     if (st) {
         float k = 0, t = 0;
         cudaEventElapsedTime(&k, s->ev[0], s->ev[2]); cudaEventElapsedTime(&t, s->ev[0], s->ev[3]);
@@ -526,7 +528,7 @@ int rt_render_accumulate_device(RtScene* s, const RtRenderParams* p, float* accu
     CUDA_TRY(cudaEventRecord(s->ev[2], stream));
     if (st) {
         CUDA_TRY(cudaStreamSynchronize(stream));
-        if ((rc = collect_stats(s, plan, st, 2, stream)) != RT_OK) return rc;
+        if ((rc = collect_stats(s, plan, ki, st, 2, stream)) != RT_OK) return rc;
         float k = 0;
         cudaEventElapsedTime(&k, s->ev[0], s->ev[2]);
         st->kernel_ms = k; st->total_ms = k;
