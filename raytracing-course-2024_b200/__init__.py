@@ -18,7 +18,7 @@ import subprocess
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "_build", "librt_b200.so")
+LIB_PATH = os.environ.get("RT_B200_LIB") or os.path.join(_HERE, "_build", "librt_b200.so")   # env override: A/B builds of the same ABI
 CLI_PATH = os.path.join(_HERE, "_build", "raytracing-engine")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "rt_api.h")
 

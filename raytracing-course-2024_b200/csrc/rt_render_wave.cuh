@@ -21,6 +21,9 @@
 #pragma once
 
 #define RT_POOL_SLOTS 64
+#ifndef RT_NODE_UNROLL
+#define RT_NODE_UNROLL 3   /* box-pair steps per phase vote */
+#endif
 // Slot fields (words, SoA [field][slot]).  A slot is read by the shade round and by the lane that traces its ray, never
 // by both at once, so hand-over fields share storage:
 //   shade -> trace: O (ray origin), D (direction), IV (safe reciprocal direction), F_TRI = triangle to skip (or -1)
@@ -300,6 +303,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 for (;;) {
                     if (__popc(__ballot_sync(FULL, cur >= 0)) < nmin) break;
                     if (cur >= 0) node_step();
+#if RT_NODE_UNROLL >= 2
+                    if (cur >= 0) node_step();
+#endif
+#if RT_NODE_UNROLL >= 3
+                    if (cur >= 0) node_step();
+#endif
                 }
                 const bool at_leaf = cur < 0 && cur != RT_CUR_DONE;
                 if (__ballot_sync(FULL, at_leaf) == 0u) break;                   // fewer than nmin box-pair lanes, the rest finished
