@@ -5,6 +5,7 @@
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
+#include <limits>
 #include <map>
 #include <string>
 #include <vector>
@@ -65,6 +66,21 @@ struct BlobWriter {
 };
 
 inline float i2f(int32_t i) { float f; std::memcpy(&f, &i, 4); return f; }
+
+// Ray-independent part of the triangle test (rt_device.cuh TriTest), evaluated in f64: unit normal N, vertex a, and the
+// barycentric gradients Au = (e2 x Nu)/|Nu|^2, Av = (Nu x e1)/|Nu|^2 with Nu = e1 x e2.  out12 = N, a, Au, Av.
+void tri_test_record(const double* v, float* out12) {
+    double e1[3], e2[3];
+    for (int a = 0; a < 3; ++a) { e1[a] = v[3 + a] - v[a]; e2[a] = v[6 + a] - v[a]; }
+    const double nu[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+    const double n2 = nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2], len = std::sqrt(n2);
+    const double au[3] = {e2[1] * nu[2] - e2[2] * nu[1], e2[2] * nu[0] - e2[0] * nu[2], e2[0] * nu[1] - e2[1] * nu[0]};
+    const double av[3] = {nu[1] * e1[2] - nu[2] * e1[1], nu[2] * e1[0] - nu[0] * e1[2], nu[0] * e1[1] - nu[1] * e1[0]};
+    for (int a = 0; a < 3; ++a) {
+        out12[a] = (float)(nu[a] / len); out12[3 + a] = (float)v[a];
+        out12[6 + a] = (float)(au[a] / n2); out12[9 + a] = (float)(av[a] / n2);
+    }
+}
 
 // FlatBvh (box_a/box_b/box_c/child, host_scene.h) -> the device's octant-ordered pair nodes (rt_device.cuh, RT_NODE_BYTES):
 // per axis (c0.min c1.min c0.max c1.max | c0.max c1.max c0.min c1.min), then the two child references.
@@ -145,6 +161,7 @@ int flatten_scene(RtScene* s) {
     // BVH-ordered triangle + shading arrays
     const int nt = n > 0 ? n : 1;   // an empty scene keeps one degenerate triangle (never hit: det == 0)
     std::vector<float> tri_a((size_t)nt * 4, 0.f), tri_e1((size_t)nt * 4, 0.f), tri_e2((size_t)nt * 4, 0.f);
+    std::vector<float> tri_t((size_t)nt * 12, std::numeric_limits<float>::quiet_NaN());
     std::vector<float> sh_n0((size_t)nt * 4, 0.f), sh_dn1((size_t)nt * 4, 0.f), sh_dn2((size_t)nt * 4, 0.f), sh_ng((size_t)nt * 4, 0.f);
     s->tri_d_host.assign((size_t)nt * 9, 0.0);
     sh_dn1[3] = i2f(-1);
@@ -156,6 +173,7 @@ int flatten_scene(RtScene* s) {
         for (int a = 0; a < 3; ++a) { e1[a] = v[3 + a] - v[a]; e2[a] = v[6 + a] - v[a]; }
         double ng[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
         const double len = std::sqrt(ng[0] * ng[0] + ng[1] * ng[1] + ng[2] * ng[2]);
+        tri_test_record(v, &tri_t[(size_t)k * 12]);
         for (int a = 0; a < 3; ++a) {
             tri_a[(size_t)k * 4 + (size_t)a] = (float)v[a];
             tri_e1[(size_t)k * 4 + (size_t)a] = (float)e1[a];
@@ -173,7 +191,8 @@ int flatten_scene(RtScene* s) {
     }
     // light arrays (device light order)
     const int nl = n_lights > 0 ? n_lights : 1;
-    std::vector<float> lt_a((size_t)nl * 4, 0.f), lt_e1((size_t)nl * 4, 0.f), lt_e2((size_t)nl * 4, 0.f), lt_ng((size_t)nl * 4, 0.f);
+    std::vector<float> lt_a((size_t)nl * 4, 0.f), lt_e1((size_t)nl * 4, 0.f), lt_e2((size_t)nl * 4, 0.f);
+    std::vector<float> lt_t((size_t)nl * 16, std::numeric_limits<float>::quiet_NaN());
     for (int k = 0; k < n_lights; ++k) {
         const int id = s->light_order[(size_t)k];
         const double* v = &h.tri_v[(size_t)id * 9];
@@ -185,9 +204,12 @@ int flatten_scene(RtScene* s) {
             lt_a[(size_t)k * 4 + (size_t)a] = (float)v[a];
             lt_e1[(size_t)k * 4 + (size_t)a] = (float)e1[a];
             lt_e2[(size_t)k * 4 + (size_t)a] = (float)e2[a];
-            lt_ng[(size_t)k * 4 + (size_t)a] = (float)(ng[a] / len);
         }
-        lt_a[(size_t)k * 4 + 3] = (float)(1.0 / (len * 0.5));     // get_local_pdf distributions.rs:76-79
+        float rec[12];
+        tri_test_record(v, rec);
+        for (int q = 0; q < 4; ++q) for (int a = 0; a < 3; ++a) lt_t[(size_t)k * 16 + (size_t)q * 4 + (size_t)a] = rec[q * 3 + a];
+        lt_t[(size_t)k * 16 + 3] = (float)(1.0 / (len * 0.5));    // 1/area, get_local_pdf distributions.rs:76-79
+        lt_t[(size_t)k * 16 + 7] = lt_t[(size_t)k * 16 + 11] = lt_t[(size_t)k * 16 + 15] = 0.f;
     }
 
     s->blob_host.clear();
@@ -196,6 +218,7 @@ int flatten_scene(RtScene* s) {
     std::memset(&L, 0, sizeof(L));
     const std::vector<float> nodes = octant_nodes(s->bvh);
     L.nodes = w.add(nodes.data(), nodes.size() * 4);
+    L.tri_t = w.add(tri_t.data(), tri_t.size() * 4);
     L.tri_a = w.add(tri_a.data(), tri_a.size() * 4);
     L.tri_e1 = w.add(tri_e1.data(), tri_e1.size() * 4);
     L.tri_e2 = w.add(tri_e2.data(), tri_e2.size() * 4);
@@ -208,7 +231,7 @@ int flatten_scene(RtScene* s) {
     L.lt_a = w.add(lt_a.data(), lt_a.size() * 4);
     L.lt_e1 = w.add(lt_e1.data(), lt_e1.size() * 4);
     L.lt_e2 = w.add(lt_e2.data(), lt_e2.size() * 4);
-    L.lt_ng = w.add(lt_ng.data(), lt_ng.size() * 4);
+    L.lt_t = w.add(lt_t.data(), lt_t.size() * 4);
     if (use_light_bvh) {
         const std::vector<float> lnodes = octant_nodes(s->light_bvh);
         L.lnodes = w.add(lnodes.data(), lnodes.size() * 4);

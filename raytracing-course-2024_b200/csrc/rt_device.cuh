@@ -54,10 +54,12 @@ RT_DEV float u01(uint32_t x) { return (float)(x >> 8) * (1.0f / 16777216.0f); } 
 // CTA when it fits (practice7_4: ~12 KB) and read it with ld.shared -- same code, different Space.
 struct SceneLayout {
     uint32_t nodes;                              // finite-primitive BVH: octant-ordered child-pair nodes, RT_NODE_BYTES each (below)
-    uint32_t tri_a, tri_e1, tri_e2;              // BVH-ordered triangles: a, b-a, c-a (w unused)
+    uint32_t tri_t;                              // BVH-ordered triangle TEST records, 48 bytes each (TriTest below)
+    uint32_t tri_a, tri_e1, tri_e2;              // BVH-ordered triangles: a, b-a, c-a (w unused) -- hit-point evaluation
     uint32_t sh_n0, sh_dn1, sh_dn2, sh_ng;       // a_norm|material id, b_norm-a_norm|orig id, c_norm-a_norm, unit face normal
     uint32_t mat0, mat1;                         // base rgb|metallic, emission rgb|roughness
-    uint32_t lt_a, lt_e1, lt_e2, lt_ng;          // light triangles (light-BVH order): a|1/area, e1, e2, unit normal
+    uint32_t lt_a, lt_e1, lt_e2;                 // light triangles (light-BVH order): a, e1, e2 -- point sampling
+    uint32_t lt_t;                               // light TEST records, 64 bytes each: N|1/area, a, Au, Av
     uint32_t lnodes;                             // light BVH, same node format (used when n_lights > RT_BRUTE_LIGHTS)
     uint32_t total_bytes;
     int32_t n_nodes, n_tris, n_mats, n_lights, n_lnodes;
@@ -181,18 +183,28 @@ RT_DEV void pair_step(const Space& sp, uint32_t nodes, const RaySetup& r, float 
         : "f"(t0), "f"(t1), "f"(e0), "f"(e1), "r"(ch.x), "r"(ch.y), "r"(st.stride), "f"(ORDERED ? t0 : t1));
 }
 
-// Two-sided ray/triangle test with inclusive edges: u >= 0, v >= 0, u + v <= 1, t > 0 (geometry.rs:109-113).
-// The reference solves the 3x3 system with Matrix3::try_inverse; this is the same solution by Cramer's rule on
-// precomputed edges (Moller-Trumbore form).  det == 0 -> inf/NaN -> every comparison fails, like try_inverse.
-RT_DEV bool tri_test(float3 o, float3 d, float3 a, float3 e1, float3 e2, float& t, float& u, float& v) {
-    float3 pvec = cross(d, e2);
-    float det = dot(e1, pvec);
-    float inv_det = fast_rcp(det);
-    float3 tvec = o - a;
-    float3 qvec = cross(tvec, e1);
-    u = dot(tvec, pvec) * inv_det;
-    v = dot(d, qvec) * inv_det;
-    t = dot(e2, qvec) * inv_det;
+// Two-sided ray/triangle test with inclusive edges: u >= 0, v >= 0, u + v <= 1, t > 0 (geometry.rs:109-113).  The
+// reference solves [b-a, c-a, -d] (u,v,t)^T = o-a with Matrix3::try_inverse (geometry.rs:103-111).  Here the
+// ray-independent part of that solution is precomputed per triangle on the host in f64 (TriTest):
+//   N  = unit normal of (e1 x e2),  Au = (e2 x Nu)/|Nu|^2,  Av = (Nu x e1)/|Nu|^2   with Nu = e1 x e2,
+// so that   t = N.(a-o) / N.d,   Q = o + t d - a,   u = Au.Q,   v = Av.Q   (19 flops + 1 rcp instead of 30 + 1).
+// N.d == 0 (the reference's det == 0) -> inf/NaN -> the strict `t < best` / the comparisons reject it; a degenerate
+// triangle has non-finite Au/Av and is never hit, like try_inverse failing.
+struct TriTest { float3 N, a, Au, Av; };
+template <class Space>
+RT_DEV TriTest load_tri_test(const Space& sp, uint32_t tri_t, int i) {     // packed 48-byte record
+    const uint32_t o = tri_t + (uint32_t)i * 48u;
+    const float4 r0 = sp.ld4(o), r1 = sp.ld4(o + 16u), r2 = sp.ld4(o + 32u);
+    TriTest T;
+    T.N = f3(r0.x, r0.y, r0.z); T.a = f3(r0.w, r1.x, r1.y); T.Au = f3(r1.z, r1.w, r2.x); T.Av = f3(r2.y, r2.z, r2.w);
+    return T;
+}
+RT_DEV bool tri_test(float3 o, float3 d, const TriTest& T, float& t, float& u, float& v) {
+    const float3 oa = T.a - o;
+    t = dot(T.N, oa) * fast_rcp(dot(T.N, d));
+    const float3 Q = fma3(d, t, -oa);
+    u = dot(T.Au, Q);
+    v = dot(T.Av, Q);
     // Edges are inclusive in the reference (f64, effectively watertight).  In FP32 the two triangles sharing an
     // edge can both round a ray just outside; a 2e-6 barycentric overlap closes those cracks for well-conditioned
     // triangles (overlap is harmless: the nearest hit still wins).
@@ -223,10 +235,8 @@ RT_DEV void trace_nearest(const Space& sp, const SceneLayout& L, SmemStack& st, 
         const uint32_t code = (uint32_t)~cur;
         const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
         for (int i = first; i < first + n; ++i) {
-            const uint32_t o16 = (uint32_t)i * 16u;
-            const float4 a = sp.ld4(L.tri_a + o16), e1 = sp.ld4(L.tri_e1 + o16), e2 = sp.ld4(L.tri_e2 + o16);
             float t, u, v;
-            const bool ok = tri_test(o, d, f3(a), f3(e1), f3(e2), t, u, v);
+            const bool ok = tri_test(o, d, load_tri_test(sp, L.tri_t, i), t, u, v);
             if (STATS) cnt.tri_tests += 1;
             if (ok && t < hit.t && i != skip_tri) { hit.t = t; hit.u = u; hit.v = v; hit.tri = i; }
         }
@@ -321,13 +331,13 @@ RT_DEV float3 sample_light(const Space& sp, const SceneLayout& L, float3 point, 
 // (1/area) * |p - point|^2 / |ng . omega| for a ray that pierces it at t > 0 (both faces, no occlusion).
 template <class Space>
 RT_DEV float light_tri_pdf(const Space& sp, const SceneLayout& L, int i, float3 point, float3 l) {
-    const uint32_t o16 = (uint32_t)i * 16u;
-    const float4 a = sp.ld4(L.lt_a + o16);
-    const float3 e1 = f3(sp.ld4(L.lt_e1 + o16)), e2 = f3(sp.ld4(L.lt_e2 + o16));
+    const uint32_t o = L.lt_t + (uint32_t)i * 64u;
+    const float4 r0 = sp.ld4(o);
+    TriTest T;
+    T.N = f3(r0); T.a = f3(sp.ld4(o + 16u)); T.Au = f3(sp.ld4(o + 32u)); T.Av = f3(sp.ld4(o + 48u));
     float t, u, v;
-    if (!tri_test(point, l, f3(a), e1, e2, t, u, v)) return 0.0f;
-    const float3 ng = f3(sp.ld4(L.lt_ng + o16));
-    return a.w * t * t * fast_rcp(fabsf(dot(ng, l)));   // l is unit: |p - point|^2 = t^2, omega = l
+    if (!tri_test(point, l, T, t, u, v)) return 0.0f;
+    return r0.w * t * t * fast_rcp(fabsf(dot(T.N, l)));   // l is unit: |p - point|^2 = t^2, omega = l, N = unit normal
 }
 
 // MultipleLightSamplingDistribution::pdf (distributions.rs:160-184): sum over ALL light triangles the ray

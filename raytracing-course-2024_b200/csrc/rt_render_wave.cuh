@@ -106,10 +106,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
         const float3 o = pool.ld3(F_OX, slot), d = pool.ld3(F_DX, slot);
         const int skip_tri = pool.ldi(F_TRI, slot);
         for (int i = first; i < first + n; ++i) {
-            const uint32_t o16 = (uint32_t)i * 16u;
-            const float4 ta = sp.ld4(L.tri_a + o16), e1 = sp.ld4(L.tri_e1 + o16), e2 = sp.ld4(L.tri_e2 + o16);
             float t, u, v;
-            const bool ok = tri_test(o, d, f3(ta), f3(e1), f3(e2), t, u, v);
+            const bool ok = tri_test(o, d, load_tri_test(sp, L.tri_t, i), t, u, v);
             if (STATS) cnt.tri_tests += 1;
             if (ok && t < t_best && i != skip_tri) { t_best = t; hit_tri = i; pool.stf(F_U, slot, u); pool.stf(F_V, slot, v); }
         }
