@@ -308,6 +308,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     if (s0 == 0 && s1 == 0) s1 = h.samples;
     if (s0 < 0 || s1 > h.samples || s0 >= s1) return fail(RT_ERR_INVALID, "sample range must satisfy 0 <= begin < end <= samples");
     if ((uint64_t)h.width * (uint64_t)h.height > (1ull << 30)) return fail(RT_ERR_LIMIT, "frame larger than 2^30 pixels");
+    if (h.width > 65535 || h.height > 65535) return fail(RT_ERR_LIMIT, "frame dimensions above 65535 (pixel coordinates are packed in 16 bits)");
     CUDA_TRY(cudaSetDevice(s->device));
 
     rtd::RenderArgs& a = plan->args;

@@ -34,7 +34,7 @@
 enum { F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_IX, F_IY, F_IZ, F_TRI, F_U, F_V, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ, F_PIX, F_S, F_CHUNK, F_META, NF };
 #define RT_POOL_QUEUE_BYTES (2u * RT_POOL_SLOTS)                       /* TQ and SQ: one byte per entry */
 #define RT_POOL_WARP_BYTES (RT_POOL_SLOTS * NF * 4u + RT_POOL_QUEUE_BYTES)
-enum { ST_NEED_ITEM = 0, ST_NEED_PATH = 1, ST_GEN = 2, ST_TRACE = 3, ST_RETRY = 4, ST_EXHAUSTED = 5, ST_NONE = 6 };
+enum { ST_NEED_ITEM = 0, ST_ENDED = 1, ST_GEN = 2, ST_TRACE = 3, ST_RETRY = 4, ST_EXHAUSTED = 5, ST_NONE = 6 };
 
 struct Pool {
     uint32_t base;
@@ -155,81 +155,49 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 }
                 sq_head = (sq_head + n_take) & (P - 1);
                 sq_n -= n_take;
-                if (state == ST_TRACE || state == ST_RETRY) {                    // get_ray_color (rendering.rs:86-127), one attempt
-                    int depth = (int)((meta >> 3) & 0xffu), attempt = (int)((meta >> 11) & 0x7fu);
-                    uint32_t call = meta >> 18;
-                    const int tri = pool.ldi(F_TRI, s);
-                    float3 T = pool.ld3(F_TX, s);
-                    bool end_path = false;
+                int depth = (int)((meta >> 3) & 0xffu), attempt = (int)((meta >> 11) & 0x7fu);
+                uint32_t call = meta >> 18;
+                int tri = -1, mat_id = 0;
+                float4 n0 = make_float4(0.f, 0.f, 0.f, 0.f);
+                float3 T = f3(1.f, 1.f, 1.f);
+
+                // (1) what the nearest-hit query returned: get_ray_color (rendering.rs:86-127) up to the sampling loop
+                bool ends = state == ST_ENDED;
+                if (state == ST_TRACE || state == ST_RETRY) {
+                    tri = pool.ldi(F_TRI, s);
+                    T = pool.ld3(F_TX, s);
                     if (tri < 0) {                                               // :125
                         if (bg_nonzero) pool.st3(F_AX, s, pool.ld3(F_AX, s) + T * bg);
-                        end_path = true;
+                        ends = true;
                     } else {
-                        const uint32_t o16 = (uint32_t)tri * 16u;
-                        const float4 n0 = sp.ld4(L.sh_n0 + o16);
-                        const Material mat = load_material(sp, L, __float_as_int(n0.w));
+                        n0 = sp.ld4(L.sh_n0 + (uint32_t)tri * 16u);
+                        mat_id = __float_as_int(n0.w);
                         if (attempt == 0) {
-                            if ((mat.emission.x != 0.f) | (mat.emission.y != 0.f) | (mat.emission.z != 0.f))
-                                pool.st3(F_AX, s, pool.ld3(F_AX, s) + T * mat.emission);   // :99
-                            if (--depth <= 0) end_path = true;                   // :93-95
+                            const float3 em = f3(sp.ld4(L.mat1 + (uint32_t)mat_id * 16u));
+                            if ((em.x != 0.f) | (em.y != 0.f) | (em.z != 0.f)) pool.st3(F_AX, s, pool.ld3(F_AX, s) + T * em);   // :99
+                            if (--depth <= 0) ends = true;                       // :93-95
                             else if (STATS) ++c_vertices;
                         }
-                        if (!end_path) {
-                            const float3 rd = pool.ld3(F_DX, s);
-                            const float hu = pool.ldf(F_U, s), hv = pool.ldf(F_V, s);
-                            const float3 ng = f3(sp.ld4(L.sh_ng + o16));
-                            const float sgn = dot(ng, rd) < 0.0f ? 1.0f : -1.0f; // geometry.rs:115-126
-                            const float3 n = ng * sgn;
-                            const float3 dn1 = f3(sp.ld4(L.sh_dn1 + o16)), dn2 = f3(sp.ld4(L.sh_dn2 + o16));
-                            const float3 ns = (f3(n0) + dn1 * hu + dn2 * hv) * sgn;
-                            const float3 ta = f3(sp.ld4(L.tri_a + o16)), te1 = f3(sp.ld4(L.tri_e1 + o16)), te2 = f3(sp.ld4(L.tri_e2 + o16));
-                            const float3 Pt = fma3(rd, -RT_EPS_F, fma3(te2, hv, fma3(te1, hu, ta)));   // :98
-                            const float3 v = -rd;
-                            const float nv = dot(n, v);
-                            const float alpha = mat.roughness * mat.roughness, alpha2 = alpha * alpha;
-                            const float g1v = ggx_g1(nv, alpha2);
-                            const uint32_t pix = (uint32_t)pool.ldi(F_PIX, s);
-                            const int s_this = pool.ldi(F_S, s);
-                            const uint4 rnd = philox4x32_10(make_uint4(pix, (uint32_t)s_this, call, RT_PHILOX_TAG), key);
-                            call = (call + 1u) & 0x3fffu;
-                            float3 l; DirTerms terms;
-                            const float pdf = mix_sample_and_pdf<Space, STATS>(sp, L, st, a.n_comp, Pt, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
-                            ++attempt;
-                            if (STATS) ++c_attempts;
-                            if (pdf > 0.0f && dot(l, ns) > 0.0f) {               // :107
-                                const float d_chi = terms.nh > 0.0f ? terms.d_nochi : 0.0f;
-                                const float3 f = brdf_eval(mat, d_chi, ggx_g1(terms.nl, alpha2), g1v, terms.nl, nv, terms.hl);
-                                T = T * f * (terms.nl * fast_rcp(pdf));          // :122
-                                if (!finite3(T)) { if (STATS) ++c_nonfinite; end_path = true; }
-                                else {
-                                    pool.st3(F_OX, s, Pt); pool.st3(F_DX, s, l); pool.st3(F_IX, s, safe_inv_dir(l)); pool.st3(F_TX, s, T);
-                                    pool.sti(F_TRI, s, terms.nl > 0.0f ? tri : -1);
-                                    attempt = 0; state = ST_TRACE;
-                                }
-                            } else if (attempt >= a.max_attempts || attempt >= 127) {
-                                if (STATS) ++c_cap;
-                                end_path = true;
-                            } else {
-                                state = ST_RETRY;
-                            }
-                        }
                     }
-                    if (end_path) state = ST_NEED_PATH;
-                    meta = pack_meta(state, depth, attempt, call);
                 }
-                if (state == ST_NEED_PATH) {                                     // next sample of this item, or store the item
+                // (2) path bookkeeping for the slots whose path ended: next sample of the item, or store the item and
+                //     fetch a new one (warp-aggregated atomic on the frame's work counter)
+                uint32_t xy = 0;
+                int s_this = 0;
+                if (state != ST_NONE && state != ST_NEED_ITEM) { xy = (uint32_t)pool.ldi(F_PIX, s); s_this = pool.ldi(F_S, s); }
+                if (ends) {
                     const int chunk = pool.ldi(F_CHUNK, s);
-                    const int s_next = pool.ldi(F_S, s) + 1, s_stop = min(a.s_begin + (chunk + 1) * a.chunk_size, a.s_end);
-                    if (s_next < s_stop) { pool.sti(F_S, s, s_next); state = ST_GEN; }
+                    const int s_stop = min(a.s_begin + (chunk + 1) * a.chunk_size, a.s_end);
+                    if (++s_this < s_stop) state = ST_GEN;
                     else {
-                        const uint32_t pix = (uint32_t)pool.ldi(F_PIX, s);
+                        const uint32_t pix = (xy >> 16) * (uint32_t)a.W + (xy & 0xffffu);
                         const float3 acc = pool.ld3(F_AX, s);
                         const float n_done = (float)(s_stop - (a.s_begin + chunk * a.chunk_size));
                         a.layers[(size_t)chunk * n_pix + pix] = make_float4(acc.x, acc.y, acc.z, n_done);
                         state = ST_NEED_ITEM;
                     }
                 }
-                for (;;) {                                                       // warp-aggregated work fetch
+                for (;;) {
                     const bool need = state == ST_NEED_ITEM;
                     const unsigned m = __ballot_sync(FULL, need);
                     if (m == 0u) break;
@@ -245,39 +213,82 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                             const uint32_t rr = idx - chunk * a.n_pix_items;
                             const uint32_t tile = rr >> 5, w = rr & 31u;
                             const uint32_t ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
-                            const int px = (int)(tx * 8u + (w & 7u)), py = (int)(ty * 4u + (w >> 3));
-                            if (px < a.W && py < a.H) {
-                                const int s0 = a.s_begin + (int)chunk * a.chunk_size;
-                                pool.sti(F_PIX, s, (int)((uint32_t)py * (uint32_t)a.W + (uint32_t)px));
+                            const uint32_t px = tx * 8u + (w & 7u), py = ty * 4u + (w >> 3);
+                            if ((int)px < a.W && (int)py < a.H) {
+                                xy = (py << 16) | px;
+                                s_this = a.s_begin + (int)chunk * a.chunk_size;
+                                pool.sti(F_PIX, s, (int)xy);
                                 pool.sti(F_CHUNK, s, (int)chunk);
-                                pool.sti(F_S, s, s0);
                                 pool.st3(F_AX, s, f3(0.f, 0.f, 0.f));
                                 state = ST_GEN;
                             }
                         }
                     }
                 }
-                if (state == ST_GEN) {                                           // get_ray_to_pixel (rendering.rs:71-84)
-                    const uint32_t pix = (uint32_t)pool.ldi(F_PIX, s);
-                    const int s_this = pool.ldi(F_S, s);
-                    const int py = (int)(pix / (uint32_t)a.W), px = (int)(pix - (uint32_t)py * (uint32_t)a.W);
-                    const uint4 rr = philox4x32_10(make_uint4(pix, (uint32_t)s_this, 0u, RT_PHILOX_TAG), key);
-                    float3 co, cd;
-                    camera_ray(a.cam, a.W, a.H, px, py, u01(rr.x), u01(rr.y), co, cd);
-                    pool.st3(F_OX, s, co); pool.st3(F_DX, s, cd); pool.st3(F_IX, s, safe_inv_dir(cd)); pool.st3(F_TX, s, f3(1.f, 1.f, 1.f));
-                    pool.sti(F_TRI, s, -1);
-                    state = ST_TRACE;
-                    meta = pack_meta(state, a.ray_depth > 255 ? 255 : a.ray_depth, 0, 1u);
+                if (state == ST_GEN) {
+                    pool.sti(F_S, s, s_this);
+                    call = 0u; attempt = 0; depth = a.ray_depth > 255 ? 255 : a.ray_depth;
                     if (STATS) ++c_samples;
-                } else {
-                    meta = (meta & ~7u) | (uint32_t)state;
                 }
-                if (state != ST_NONE) pool.sti(F_META, s, (int)meta);
+                // (3) ONE Philox call per live slot: the camera jitter of a new path (call 0) or the next attempt of the
+                //     rejection loop (call >= 1)
+                const bool live = state == ST_GEN || state == ST_TRACE || state == ST_RETRY;
+                uint4 rnd = make_uint4(0u, 0u, 0u, 0u);
+                const uint32_t pix = (xy >> 16) * (uint32_t)a.W + (xy & 0xffffu);
+                if (live) { rnd = philox4x32_10(make_uint4(pix, (uint32_t)s_this, call, RT_PHILOX_TAG), key); call = (call + 1u) & 0x3fffu; }
+                // (4) the new ray: camera ray (rendering.rs:71-84), or one attempt of the rejection loop (:102-110)
+                float3 ro = f3(0.f, 0.f, 0.f), rd = f3(0.f, 0.f, 1.f);
+                int skip = -1;
+                bool accepted = false;
+                if (state == ST_GEN) {
+                    camera_ray(a.cam, a.W, a.H, (int)(xy & 0xffffu), (int)(xy >> 16), u01(rnd.x), u01(rnd.y), ro, rd);
+                    T = f3(1.f, 1.f, 1.f);
+                    accepted = true;
+                } else if (live) {
+                    const uint32_t o16 = (uint32_t)tri * 16u;
+                    const Material mat = load_material(sp, L, mat_id);
+                    const float3 din = pool.ld3(F_DX, s);
+                    const float hu = pool.ldf(F_U, s), hv = pool.ldf(F_V, s);
+                    const float3 ng = f3(sp.ld4(L.sh_ng + o16));
+                    const float sgn = dot(ng, din) < 0.0f ? 1.0f : -1.0f;         // geometry.rs:115-126
+                    const float3 n = ng * sgn;
+                    const float3 dn1 = f3(sp.ld4(L.sh_dn1 + o16)), dn2 = f3(sp.ld4(L.sh_dn2 + o16));
+                    const float3 ns = (f3(n0) + dn1 * hu + dn2 * hv) * sgn;
+                    const float3 ta = f3(sp.ld4(L.tri_a + o16)), te1 = f3(sp.ld4(L.tri_e1 + o16)), te2 = f3(sp.ld4(L.tri_e2 + o16));
+                    const float3 Pt = fma3(din, -RT_EPS_F, fma3(te2, hv, fma3(te1, hu, ta)));   // :98
+                    const float3 v = -din;
+                    const float nv = dot(n, v);
+                    const float alpha = mat.roughness * mat.roughness, alpha2 = alpha * alpha;
+                    const float g1v = ggx_g1(nv, alpha2);
+                    float3 l; DirTerms terms;
+                    const float pdf = mix_sample_and_pdf<Space, STATS>(sp, L, st, a.n_comp, Pt, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
+                    ++attempt;
+                    if (STATS) ++c_attempts;
+                    if (pdf > 0.0f && dot(l, ns) > 0.0f) {                       // :107
+                        const float d_chi = terms.nh > 0.0f ? terms.d_nochi : 0.0f;
+                        const float3 f = brdf_eval(mat, d_chi, ggx_g1(terms.nl, alpha2), g1v, terms.nl, nv, terms.hl);
+                        T = T * f * (terms.nl * fast_rcp(pdf));                  // :122
+                        if (!finite3(T)) { if (STATS) ++c_nonfinite; state = ST_ENDED; }
+                        else { ro = Pt; rd = l; skip = terms.nl > 0.0f ? tri : -1; attempt = 0; accepted = true; }
+                    } else if (attempt >= a.max_attempts || attempt >= 127) {
+                        if (STATS) ++c_cap;
+                        state = ST_ENDED;                                        // the path ends in the next round
+                    } else {
+                        state = ST_RETRY;
+                    }
+                }
+                if (accepted) {
+                    pool.st3(F_OX, s, ro); pool.st3(F_DX, s, rd); pool.st3(F_IX, s, safe_inv_dir(rd)); pool.st3(F_TX, s, T);
+                    pool.sti(F_TRI, s, skip);
+                    state = ST_TRACE;
+                }
+                if (state != ST_NONE) pool.sti(F_META, s, (int)pack_meta(state, depth, attempt, call));
                 const unsigned to_tq = __ballot_sync(FULL, state == ST_TRACE);
                 if (state == ST_TRACE) pool.qst(0, (tq_head + tq_n + __popc(to_tq & lt_mask)) & (P - 1), s);
                 tq_n += __popc(to_tq);
-                const unsigned to_sq = __ballot_sync(FULL, state == ST_RETRY);   // rejected attempt: retry in a later round
-                if (state == ST_RETRY) pool.qst(1, (sq_head + sq_n + __popc(to_sq & lt_mask)) & (P - 1), s);
+                const bool again = state == ST_RETRY || state == ST_ENDED;       // rejected attempt / late path end: a later round
+                const unsigned to_sq = __ballot_sync(FULL, again);
+                if (again) pool.qst(1, (sq_head + sq_n + __popc(to_sq & lt_mask)) & (P - 1), s);
                 sq_n += __popc(to_sq);
                 __syncwarp();
                 continue;
