@@ -217,6 +217,14 @@ def sample_vndf(n, v, rough, u12):
     return out
 
 
+def sample_vndf_cap(n, v, rough, u12):
+    """The DEVICE's VNDF sampler (spherical caps), f64 restatement -- not a reference function; see oracle.cpp."""
+    n, v, rough, u12 = _d(n), _d(v), _d(rough), _d(u12)
+    out = np.zeros((n.shape[0], 3))
+    lib().or_sample_vndf_cap(_p(n), _p(v), _p(rough), _p(u12), C.c_int64(n.shape[0]), _p(out))
+    return out
+
+
 def color_to_pixel(rgb):
     rgb = _d(rgb)
     out = np.zeros((rgb.shape[0], 3), dtype=np.uint8)

@@ -411,6 +411,25 @@ static V3 vndf_sample_from_u(V3 n, V3 v, Fp roughness, Fp U1, Fp U2, Counters* c
     if (c && !almost_equal_vecs(global_norm, normalize(result + v))) ++c->vndf_assert_fail;   // assert! at :272
     return normalize(result);
 }
+// NOT in the reference: the device's VNDF sampler.  It draws the same visible-normal distribution as sample_ggx_vndf
+// (:209-234) with the spherical-cap construction (Dupuy & Benyoub 2023) in a branchless tangent frame (Duff et al. 2017);
+// for the isotropic alpha of the reference the distribution does not depend on the tangent frame, so it is
+// distribution-equivalent to vndf_sample_from_u (streams differ anyway: the device uses Philox).  f64 restatement used
+// to check the device on explicit uniforms; tests/test_oracle_kat.py checks it against the reference sampler statistically.
+static V3 vndf_cap_sample_from_u(V3 n, V3 v, Fp roughness, Fp U1, Fp U2) {
+    Fp sign = std::copysign(1.0, n.z), a = -1.0 / (sign + n.z), b = n.x * n.y * a;
+    V3 t1 = v3(1.0 + sign * n.x * n.x * a, sign * b, -sign * n.x), t2 = v3(b, sign + n.y * n.y * a, -n.y);
+    Fp alpha = powi2(roughness);
+    V3 vl = v3(dot(t1, v), dot(t2, v), dot(n, v));
+    V3 Vh = normalize(v3(alpha * vl.x, alpha * vl.y, vl.z));
+    Fp phi = 2.0 * FP_PI * U1;
+    Fp z = (1.0 - U2) * (1.0 + Vh.z) - Vh.z;
+    Fp r = std::sqrt(std::min(1.0, std::max(0.0, 1.0 - z * z)));
+    V3 Nh = v3(r * std::cos(phi) + Vh.x, r * std::sin(phi) + Vh.y, z + Vh.z);
+    V3 Ne = normalize(v3(alpha * Nh.x, alpha * Nh.y, std::max(0.0, Nh.z)));
+    V3 m = t1 * Ne.x + t2 * Ne.y + n * Ne.z;
+    return normalize(reflect_vec(v, m));
+}
 static Fp vndf_pdf(V3 n, V3 l, V3 v, Fp roughness) {                          // :276-297 (asserts at :283-288 not evaluated)
     Frame f = vndf_frame(n);
     V3 vl = to_local(f, v), ll = to_local(f, l);
@@ -736,6 +755,9 @@ void or_pdf_mix(void* h, const double* point, const double* n, const double* l, 
 void or_sample_cosine(const double* n, const double* sphere_unit, int64_t cnt, double* out) { for (int64_t i = 0; i < cnt; ++i) wr3(out + 3 * i, cosine_sample_from_sphere(rd3(n + 3 * i), rd3(sphere_unit + 3 * i))); }
 void or_sample_vndf(const double* n, const double* v, const double* rough, const double* u12, int64_t cnt, double* out) {
     for (int64_t i = 0; i < cnt; ++i) wr3(out + 3 * i, vndf_sample_from_u(rd3(n + 3 * i), rd3(v + 3 * i), rough[i], u12[2 * i], u12[2 * i + 1], nullptr));
+}
+void or_sample_vndf_cap(const double* n, const double* v, const double* rough, const double* u12, int64_t cnt, double* out) {
+    for (int64_t i = 0; i < cnt; ++i) wr3(out + 3 * i, vndf_cap_sample_from_u(rd3(n + 3 * i), rd3(v + 3 * i), rough[i], u12[2 * i], u12[2 * i + 1]));
 }
 // light_idx indexes the light list in LOAD order (ascending original triangle id).
 void or_sample_light(void* h, const int32_t* light_idx, const double* point, const double* uv, int64_t cnt, double* out) {

@@ -115,3 +115,39 @@ def test_triangle_and_aabb_primitives(oracle):
     hit, t, outer = oracle.aabb_first_hit([0, 0, 0], [0, 0, -1], [-1, -1, -1], [1, 1, 1])
     assert hit and not outer and t == pytest.approx(1.0, abs=1e-6)
     assert not oracle.aabb_first_hit([0, 0, 5], [0, 0, 1], [-1, -1, -1], [1, 1, 1])[0]
+
+
+@pytest.mark.parametrize("rough", [0.03, 0.2, 0.5, 1.0])
+def test_device_vndf_construction_draws_the_reference_distribution(oracle, rough):
+    """The device samples GGX visible normals with spherical caps in a Duff frame (oracle.sample_vndf_cap), the reference
+    with Heitz 2018 in its helper-axis frame (distributions.rs:209-234, 264-274 = oracle.sample_vndf).  Same
+    distribution: two-sample Kolmogorov-Smirnov on frame-independent projections of the reflected direction, and the
+    importance-sampling identity E[g(l)/pdf(l)] = integral of g against the reference's own pdf (:276-297)."""
+    from scipy import stats
+    rng = np.random.default_rng(int(rough * 1000) + 7)
+    cnt = 200_000
+    alpha = rough * rough
+    for n, v in [(N, nz([0.3, -0.2, 0.93])), (nz([0.5, -0.7, 0.2]), nz([0.9, -0.3, 0.6])), (nz([-0.2, 0.1, -0.97]), nz([0.1, 0.8, -0.4]))]:
+        if np.dot(n, v) <= 0:
+            v = nz(v - 2 * np.dot(n, v) * n)
+        nn, vv, rr = np.tile(n, (cnt, 1)), np.tile(v, (cnt, 1)), np.full(cnt, rough)
+        a = oracle.sample_vndf(nn, vv, rr, rng.random((cnt, 2)))           # reference construction
+        b = oracle.sample_vndf_cap(nn, vv, rr, rng.random((cnt, 2)))       # device construction
+        assert np.allclose(np.linalg.norm(b, axis=1), 1.0, atol=1e-12)
+        # frame built from (n, v) only: e1 = v's tangential direction, e2 = n x e1
+        e1 = nz(v - np.dot(n, v) * n); e2 = np.cross(n, e1)
+
+        def proj(l):
+            m = l + v; m /= np.linalg.norm(m, axis=1, keepdims=True)     # half vector = sampled visible normal
+            mz = m @ n
+            t2 = (1 - mz ** 2) / np.maximum(mz ** 2, 1e-300) / alpha ** 2  # tan^2(theta_m) / alpha^2: O(1) at every roughness
+            return t2, np.arctan2(m @ e2, m @ e1), l @ n
+        for pa, pb in zip(proj(a), proj(b)):
+            assert stats.ks_2samp(pa, pb).pvalue > 1e-4
+        # sampler <-> reference pdf: E_b[ 1{l.n > 0} cos / pdf ] must equal E_a[ the same ] (both estimate the same integral)
+        def est(l):
+            p = oracle.pdf_vndf(nn, l, vv, rr)
+            w = np.where((l @ n > 0) & (p > 0), np.maximum(l @ n, 0) / np.where(p > 0, p, 1), 0.0)
+            return w.mean(), w.std() / np.sqrt(cnt)
+        (ma, sa), (mb, sb) = est(a), est(b)
+        assert abs(ma - mb) < 5 * np.hypot(sa, sb) + 1e-12, (rough, ma, mb)
