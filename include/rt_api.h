@@ -165,6 +165,8 @@ int rt_eval(RtScene* scene_or_null, int32_t fn, const float* in, int64_t n, floa
 /* ---- output (main.rs:88-95) ------------------------------------------------------------------------------ */
 /* "P6\n{W} {H}\n255\n" + bytes.  append != 0 reproduces the reference's append-mode open (main.rs:62-66). */
 int rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t* rgb, int32_t append);
+/* dump_rendered_to_png (src/main.rs:75-86): the same pixels as an 8-bit RGB PNG (self-contained writer, stored deflate). */
+int rt_write_png(const char* path, int32_t width, int32_t height, const uint8_t* rgb);
 
 /* ---- roofline support ------------------------------------------------------------------------------------ */
 /* FFMA issue micro-benchmark on `device`: measured FP32 TFLOP/s (2 flop per FMA lane) and SM clock in MHz. */

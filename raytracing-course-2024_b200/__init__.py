@@ -107,6 +107,7 @@ def lib():
         L.rt_primary_rays.argtypes = [vp, C.POINTER(C.c_int32), _dp, C.c_int64, _dp]
         L.rt_eval.argtypes = [vp, C.c_int32, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_float)]
         L.rt_write_ppm.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint8), C.c_int32]
+        L.rt_write_png.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.POINTER(C.c_uint8)]
         L.rt_measure_fp32_peak.argtypes = [C.c_int32, _dp, _dp]
         L.rt_device_count.argtypes = [C.POINTER(C.c_int32)]
         _lib = L
@@ -293,3 +294,10 @@ def dump_rendered_to_ppm(scene: Scene, rendered: np.ndarray, path, append=False)
     rendered = np.ascontiguousarray(rendered, dtype=np.uint8)
     H, W = rendered.shape[0], rendered.shape[1]
     _check(lib().rt_write_ppm(os.fsencode(path), W, H, rendered.ctypes.data_as(C.POINTER(C.c_uint8)), 1 if append else 0))
+
+
+def dump_rendered_to_png(scene: Scene, rendered: np.ndarray, path):
+    """main.rs:75-86: the rendered RGB8 frame as a PNG."""
+    rendered = np.ascontiguousarray(rendered, dtype=np.uint8)
+    H, W = rendered.shape[0], rendered.shape[1]
+    _check(lib().rt_write_png(os.fsencode(path), W, H, rendered.ctypes.data_as(C.POINTER(C.c_uint8))))

@@ -60,10 +60,14 @@ int main(int argc, char** argv) {
         rt_scene_destroy(scene);
         return 1;
     }
-    if (argc > 6) {
-        const std::string alt = std::string(argv[6]) + ".ppm";
-        std::printf("PNG output is not built in; image dumped to %s instead of %s.png\n", alt.c_str(), argv[6]);
-        rt_write_ppm(alt.c_str(), width, height, rendered.data(), 0);
+    if (argc > 6) {                                                                                // main.rs:68-72
+        const std::string png = std::string(argv[6]) + ".png";
+        if (rt_write_png(png.c_str(), width, height, rendered.data()) != RT_OK) {
+            std::fprintf(stderr, "error: %s\n", rt_last_error());
+            rt_scene_destroy(scene);
+            return 1;
+        }
+        std::printf("Image dumped to %s\n", png.c_str());
     }
     rt_scene_destroy(scene);
     return 0;

@@ -648,6 +648,59 @@ int rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t*
     return ok ? RT_OK : fail(RT_ERR_IO, std::string("short write to ") + path);
 }
 
+// dump_rendered_to_png (main.rs:75-86): 8-bit RGB PNG with the same pixels as the PPM.  The reference goes through the
+// `image` crate; this writer is self-contained: one IDAT chunk holding a zlib stream of STORED deflate blocks (filter
+// type 0 on every row), CRC-32 per chunk, Adler-32 over the raw scanlines.  Any PNG reader decodes it to the same bytes.
+namespace {
+uint32_t crc32_update(uint32_t crc, const uint8_t* p, size_t n) {
+    static uint32_t table[256];
+    static bool init = false;
+    if (!init) {
+        for (uint32_t i = 0; i < 256; ++i) { uint32_t c = i; for (int k = 0; k < 8; ++k) c = (c & 1u) ? 0xEDB88320u ^ (c >> 1) : c >> 1; table[i] = c; }
+        init = true;
+    }
+    for (size_t i = 0; i < n; ++i) crc = table[(crc ^ p[i]) & 0xffu] ^ (crc >> 8);
+    return crc;
+}
+void put_be32(std::vector<uint8_t>& v, uint32_t x) { v.push_back((uint8_t)(x >> 24)); v.push_back((uint8_t)(x >> 16)); v.push_back((uint8_t)(x >> 8)); v.push_back((uint8_t)x); }
+bool write_chunk(FILE* f, const char type[4], const std::vector<uint8_t>& data) {
+    std::vector<uint8_t> head; put_be32(head, (uint32_t)data.size());
+    uint32_t crc = crc32_update(0xffffffffu, (const uint8_t*)type, 4);
+    if (!data.empty()) crc = crc32_update(crc, data.data(), data.size());
+    std::vector<uint8_t> tail; put_be32(tail, crc ^ 0xffffffffu);
+    return std::fwrite(head.data(), 1, 4, f) == 4 && std::fwrite(type, 1, 4, f) == 4 &&
+           (data.empty() || std::fwrite(data.data(), 1, data.size(), f) == data.size()) && std::fwrite(tail.data(), 1, 4, f) == 4;
+}
+}  // namespace
+
+int rt_write_png(const char* path, int32_t width, int32_t height, const uint8_t* rgb) {
+    if (!path || !rgb || width <= 0 || height <= 0) return fail(RT_ERR_INVALID, "bad argument");
+    const size_t row = (size_t)width * 3, raw_n = (row + 1) * (size_t)height;
+    if (raw_n > 0x7fffffffull) return fail(RT_ERR_LIMIT, "image too large for a single-IDAT PNG");
+    std::vector<uint8_t> raw(raw_n);
+    for (int32_t y = 0; y < height; ++y) { raw[(size_t)y * (row + 1)] = 0; std::memcpy(&raw[(size_t)y * (row + 1) + 1], rgb + (size_t)y * row, row); }
+    std::vector<uint8_t> z; z.reserve(raw_n + raw_n / 65535 * 5 + 16);
+    z.push_back(0x78); z.push_back(0x01);                                   // zlib header, no compression
+    uint32_t a1 = 1, a2 = 0;
+    for (size_t off = 0; off < raw_n;) {
+        const size_t n = std::min<size_t>(65535, raw_n - off);
+        z.push_back(off + n == raw_n ? 1 : 0);                               // BFINAL, BTYPE = 00 (stored)
+        z.push_back((uint8_t)(n & 0xff)); z.push_back((uint8_t)(n >> 8)); z.push_back((uint8_t)(~n & 0xff)); z.push_back((uint8_t)((~n >> 8) & 0xff));
+        z.insert(z.end(), raw.begin() + (long)off, raw.begin() + (long)(off + n));
+        for (size_t i = off; i < off + n; ++i) { a1 = (a1 + raw[i]) % 65521u; a2 = (a2 + a1) % 65521u; }
+        off += n;
+    }
+    put_be32(z, (a2 << 16) | a1);
+    FILE* f = std::fopen(path, "wb");
+    if (!f) return fail(RT_ERR_IO, std::string("cannot open ") + path);
+    static const uint8_t sig[8] = {0x89, 'P', 'N', 'G', 0x0d, 0x0a, 0x1a, 0x0a};
+    std::vector<uint8_t> ihdr; put_be32(ihdr, (uint32_t)width); put_be32(ihdr, (uint32_t)height);
+    ihdr.push_back(8); ihdr.push_back(2); ihdr.push_back(0); ihdr.push_back(0); ihdr.push_back(0);   // 8 bit, RGB, deflate, no filter method, no interlace
+    const bool ok = std::fwrite(sig, 1, 8, f) == 8 && write_chunk(f, "IHDR", ihdr) && write_chunk(f, "IDAT", z) && write_chunk(f, "IEND", {});
+    std::fclose(f);
+    return ok ? RT_OK : fail(RT_ERR_IO, std::string("short write to ") + path);
+}
+
 int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_mhz) {
     if (!tflops) return fail(RT_ERR_INVALID, "null argument");
     CUDA_TRY(cudaSetDevice(device));

@@ -381,7 +381,7 @@ def test_many_lights_use_the_light_bvh(gpu_rt, oracle):
 def test_cli_matches_library(gpu_rt, tmp_path):
     """raytracing-engine <scene> <w> <h> <samples> <out.ppm> (main.rs:37-43) == rt_render bytes behind the P6 header."""
     out = tmp_path / "o.ppm"
-    r = subprocess.run([gpu_rt.CLI_PATH, scene_path("practice7_1"), "40", "24", "16", str(out)], capture_output=True, text=True)
+    r = subprocess.run([gpu_rt.CLI_PATH, scene_path("practice7_1"), "40", "24", "16", str(out), str(tmp_path / "pic")], capture_output=True, text=True)
     assert r.returncode == 0, r.stderr
     assert "Scene finite primitives: 36, light sources: 2" in r.stdout and "Rendering took" in r.stdout
     data = out.read_bytes()
@@ -390,4 +390,6 @@ def test_cli_matches_library(gpu_rt, tmp_path):
     sc = gpu_rt.Scene.from_gltf(scene_path("practice7_1"), 40, 24, 16)
     img, _ = sc.render(seed=0)
     assert data[len(hdr):] == img.tobytes()
+    from PIL import Image                                               # optional 6th argument: {arg}.png with the same pixels (main.rs:68-72)
+    assert np.array_equal(np.asarray(Image.open(tmp_path / "pic.png").convert("RGB")), img)
     sc.close()

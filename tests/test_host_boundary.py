@@ -219,3 +219,16 @@ def test_cli_reports_errors_instead_of_panicking(rt, tmp_path):
     assert r.returncode == 2 and "usage" in r.stderr
     r = subprocess.run([rt.CLI_PATH, str(tmp_path / "nope.gltf"), "8", "8", "1", str(tmp_path / "o.ppm")], capture_output=True, text=True)
     assert r.returncode == 1 and "cannot read" in r.stderr
+
+
+def test_write_png_decodes_to_the_same_pixels(rt, tmp_path):
+    """dump_rendered_to_png (main.rs:75-86): any PNG reader must give back the rendered bytes; sizes that need several
+    stored-deflate blocks (> 65535 bytes) and rows that are not multiples of 4."""
+    from PIL import Image
+    rng = np.random.default_rng(5)
+    for H, W in ((3, 5), (97, 301), (1, 1)):
+        img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+        p = tmp_path / f"o_{H}x{W}.png"
+        rt.dump_rendered_to_png(None, img, str(p))
+        back = np.asarray(Image.open(p).convert("RGB"))
+        assert back.shape == img.shape and np.array_equal(back, img)
