@@ -294,6 +294,14 @@ def main():
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
+        traffic, traffic_src = None, None
+        try:                                                  # measured DRAM bytes of this exact launch (ncu, committed under profiles/)
+            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_v3b_bench_traffic.json")))
+            if (W, H, S, world, args.scene) == (3840, 2160, 1024, 1, SCENE):
+                traffic = tr["dram__bytes_read.sum"] + tr["dram__bytes_write.sum"]
+                traffic_src = "profiles/r1_v3b_bench_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launch)"
+        except Exception:
+            pass
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
             ms, cores, cdesc, _ = oracle_sample(args, args.cpu_seconds)
@@ -310,7 +318,7 @@ def main():
             "gpu_launches": args.steps * (2 * world + 1),
             "clocks": clk,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None,
-                         "traffic": None, "peak_source": "FFMA micro-benchmark measured in this process (MEASURED_PEAKS.json has no FP32 entry)",
+                         "traffic": traffic, "traffic_source": traffic_src, "peak_source": "FFMA micro-benchmark measured in this process (MEASURED_PEAKS.json has no FP32 entry)",
                          "kernel": kernel_name(kcfg), "launch": {k: kcfg[k] for k in ("block_threads", "blocks_per_sm", "grid_blocks", "regs_per_thread", "smem_bytes_per_block")},
                          "kernel_ms": kern_ms, "flop_per_sample": flop_per_sample, "per_sample": counts,
                          "flop_constants": {"node": C_NODE, "tri": C_TRI, "attempt": C_ATTEMPT, "shade": C_SHADE},
