@@ -393,3 +393,24 @@ def test_cli_matches_library(gpu_rt, tmp_path):
     from PIL import Image                                               # optional 6th argument: {arg}.png with the same pixels (main.rs:68-72)
     assert np.array_equal(np.asarray(Image.open(tmp_path / "pic.png").convert("RGB")), img)
     sc.close()
+
+
+def test_non_black_background_matches_oracle_and_both_kernels(gpu_rt, oracle):
+    """`None => scene.bg_color` (rendering.rs:125) with a non-black background (glTF scenes always load black,
+    gltf_to_scene.rs:65; the flat-scene entry point takes any colour): escaping paths carry throughput x background."""
+    fl = oracle.convert_gltf_to_scene(scene_path("practice7_1"), 32, 32, 1024)
+    fl.bg_color = np.array([0.4, 0.6, 0.9])
+    osc = oracle.OracleScene(fl)
+    ref = osc.render(seed=0, n_threads=0)
+    sc = gpu_rt.Scene.from_arrays(width=32, height=32, samples=1024, ray_depth=6, bg_color=fl.bg_color, camera_position=fl.camera_position,
+                                  camera_forward=fl.camera_forward, camera_right=fl.camera_right, camera_up=fl.camera_up, camera_fov_x=fl.camera_fov_x,
+                                  camera_fov_y=fl.camera_fov_y, tri_v=fl.tri_v, tri_n=fl.tri_n, tri_material=fl.tri_material, tri_emission=fl.tri_emission)
+    a, _ = sc.render_linear(seed=9, kernel_variant=10)
+    b, _ = sc.render_linear(seed=9, kernel_variant=30)
+    assert np.allclose(a, b, rtol=2e-3, atol=2e-4), float(np.abs(a - b).max())
+    lg, lr = _lum(b.astype(np.float64)).mean(), _lum(ref["mean"]).mean()
+    assert abs(lg - lr) / lr < 0.02, (lg, lr)
+    black = gpu_rt.Scene.from_gltf(scene_path("practice7_1"), 32, 32, 1024)
+    c, _ = black.render_linear(seed=9)
+    assert _lum(b.astype(np.float64)).mean() > 1.05 * _lum(c.astype(np.float64)).mean()      # the background really contributes
+    sc.close(); black.close()
