@@ -84,6 +84,27 @@ void tri_test_record(const double* v, float* out12) {
 
 // FlatBvh (box_a/box_b/box_c/child, host_scene.h) -> the device's octant-ordered pair nodes (rt_device.cuh, RT_NODE_BYTES):
 // per axis (c0.min c1.min c0.max c1.max | c0.max c1.max c0.min c1.min), then the two child references.
+// Outward rounding of a box plane whose low mantissa byte is replaced by `payload`: the result is <= v (lower = true) or
+// >= v (lower = false) and differs from v by less than 2^-14 relative.
+float plane_with_payload(float v, uint32_t payload, bool lower) {
+    if (!lower) return -plane_with_payload(-v, payload, true);
+    uint32_t bits; std::memcpy(&bits, &v, 4);
+    uint32_t out;
+    if (!(bits & 0x80000000u)) {                             // v >= +0: shrink the magnitude
+        uint32_t c = (bits & ~0xffu) | payload;
+        if (c > bits) c = bits >= 0x100u ? c - 0x100u : (0x80000000u | payload);   // tiny positive: any negative is <= v
+        out = c;
+    } else {                                                 // v < 0: grow the magnitude
+        const uint32_t mag = bits & 0x7fffffffu;
+        uint32_t c = (mag & ~0xffu) | payload;
+        if (c < mag) c += 0x100u;
+        out = 0x80000000u | c;
+    }
+    float r; std::memcpy(&r, &out, 4);
+    return r;
+}
+bool refs_packable(const rtb::FlatBvh& b) { return b.n_nodes < 32768 && b.tri_order.size() < 4096; }
+
 std::vector<float> octant_nodes(const rtb::FlatBvh& b) {
     const size_t wpn = RT_NODE_BYTES / 4;
     std::vector<float> out((size_t)std::max(b.n_nodes, 1) * wpn, 0.f);
@@ -95,6 +116,14 @@ std::vector<float> octant_nodes(const rtb::FlatBvh& b) {
             float* q = o + a * 8;
             q[0] = lo0[a]; q[1] = lo1[a]; q[2] = hi0[a]; q[3] = hi1[a];
             q[4] = hi0[a]; q[5] = hi1[a]; q[6] = lo0[a]; q[7] = lo1[a];
+        }
+        if (refs_packable(b)) {            // 16-bit references (node index / leaf code) in the low bytes of the x planes
+            const uint32_t r0 = (uint32_t)b.child[(size_t)n * 2] & 0xffffu, r1 = (uint32_t)b.child[(size_t)n * 2 + 1] & 0xffffu;
+            const uint32_t pay[4] = {r0 & 0xffu, r0 >> 8, r1 & 0xffu, r1 >> 8};
+            o[0] = plane_with_payload(o[0], pay[0], true);  o[1] = plane_with_payload(o[1], pay[1], true);     // c0.min c1.min
+            o[2] = plane_with_payload(o[2], pay[2], false); o[3] = plane_with_payload(o[3], pay[3], false);    // c0.max c1.max
+            o[4] = plane_with_payload(o[4], pay[0], false); o[5] = plane_with_payload(o[5], pay[1], false);    // c0.max c1.max
+            o[6] = plane_with_payload(o[6], pay[2], true);  o[7] = plane_with_payload(o[7], pay[3], true);     // c0.min c1.min
         }
         for (int c = 0; c < 2; ++c) {      // inner children as byte offsets (index * RT_NODE_BYTES), leaf codes unchanged
             const int32_t r = b.child[(size_t)n * 2 + (size_t)c];
@@ -245,7 +274,8 @@ int flatten_scene(RtScene* s) {
     if (need <= 96) s->stack_entries = (uint32_t)std::max(8, (need + 3) / 4 * 4);
     else return fail(RT_ERR_LIMIT, "BVH depth " + std::to_string(s->bvh.depth) + " exceeds the traversal stack");
     const int smem_limit = env_int("RT_SMEM_SCENE_MAX_BYTES", 48 * 1024);
-    s->use_smem = (int)L.total_bytes <= smem_limit;
+    L.packed_refs = refs_packable(s->bvh) ? 1 : 0;
+    s->use_smem = (int)L.total_bytes <= smem_limit && L.packed_refs;   // the shared-memory kernel reads packed references
     return RT_OK;
 }
 
@@ -333,7 +363,10 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     plan->use_smem = s->use_smem;
     const int placement = p->kernel_variant % 10, kern = p->kernel_variant / 10;
     if (placement == 1) plan->use_smem = false;
-    if (placement == 2) plan->use_smem = true;
+    if (placement == 2) {
+        if (!s->L.packed_refs) return fail(RT_ERR_LIMIT, "kernel_variant: scene too large for the shared-memory placement");
+        plan->use_smem = true;
+    }
     plan->variant = kern == 0 ? env_int("RT_KERNEL", 3) : kern;
     if (plan->variant < 1 || plan->variant > 3) return fail(RT_ERR_INVALID, "kernel_variant: unknown kernel");
 

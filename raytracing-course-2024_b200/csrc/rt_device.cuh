@@ -64,6 +64,7 @@ struct SceneLayout {
     uint32_t total_bytes;
     int32_t n_nodes, n_tris, n_mats, n_lights, n_lnodes;
     int32_t light_bvh;                           // 1: pdf walks the light BVH, 0: loops over all lights
+    int32_t packed_refs;                         // 1: the x planes of `nodes` carry 16-bit child references (pair_step PACKED)
 };
 #define RT_BRUTE_LIGHTS 8
 
@@ -121,7 +122,9 @@ RT_DEV float3 safe_inv_dir(float3 d) {
 //   [32, 64) y: same                          [64, 96) z: same
 //   [96,104) child references;  [104,112) padding
 // A child reference is >= 0 for an inner node (its BYTE offset inside the node array = index * 112, so a visit needs no
-// multiply) and < 0 for a leaf: ~((first_tri << 3) | (count - 1)).  The root is reference 0.
+// multiply) and < 0 for a leaf: ~((first_tri << 3) | (count - 1)).  The root is reference 0.  Scenes with < 32768 nodes
+// and < 4096 triangles ALSO carry 16-bit references (node index / leaf code) in the low bytes of the x planes: see
+// pair_step<.., PACKED> and SceneLayout::packed_refs.
 #define RT_NODE_BYTES 112u
 struct RaySetup {
     float3 inv, od;          // 1/d (zero components replaced, safe_inv_dir) and o/d
@@ -149,11 +152,20 @@ RT_DEV float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2
 // outward: ~20 ulps of slack for the FP32 arithmetic.  ORDERED = false: all-hits walk (children in storage order).
 // The child selection is written in PTX so that it stays in predicate registers (nvcc turns the bool algebra into
 // integer SEL / LOP3 / PRMT chains otherwise).
-template <class Space, bool ORDERED = true>
+// PACKED (small scenes, the shared-memory render kernel): node references are node INDICES / leaf codes of 16 bits, and
+// the two references of a node ride in the low mantissa bytes of the four x planes the ray loads anyway (the host rounds
+// those planes outward by up to 2^-15 relative, so the boxes stay conservative) -- the 8-byte child load disappears.
+template <class Space, bool ORDERED = true, bool PACKED = false>
 RT_DEV void pair_step(const Space& sp, uint32_t nodes, const RaySetup& r, float t_best, int& cur, SmemStack& st) {
-    const uint32_t c = (uint32_t)cur;
+    const uint32_t c = PACKED ? (uint32_t)cur * RT_NODE_BYTES : (uint32_t)cur;
     const float4 X = sp.ld4(c + r.ox), Y = sp.ld4(c + r.oy), Z = sp.ld4(c + r.oz);
-    const int2 ch = sp.ld2i(c + (nodes + 96u));
+    int2 ch;
+    if (PACKED) {
+        asm("prmt.b32 %0, %1, %2, 0xCC40;" : "=r"(ch.x) : "r"(__float_as_int(X.x)), "r"(__float_as_int(X.y)));   // sign-extended 16 bits
+        asm("prmt.b32 %0, %1, %2, 0xCC40;" : "=r"(ch.y) : "r"(__float_as_int(X.z)), "r"(__float_as_int(X.w)));
+    } else {
+        ch = sp.ld2i(c + (nodes + 96u));
+    }
     const float nx0 = fmaf(X.x, r.inv.x, -r.od.x), nx1 = fmaf(X.y, r.inv.x, -r.od.x), fx0 = fmaf(X.z, r.inv.x, -r.od.x), fx1 = fmaf(X.w, r.inv.x, -r.od.x);
     const float ny0 = fmaf(Y.x, r.inv.y, -r.od.y), ny1 = fmaf(Y.y, r.inv.y, -r.od.y), fy0 = fmaf(Y.z, r.inv.y, -r.od.y), fy1 = fmaf(Y.w, r.inv.y, -r.od.y);
     const float nz0 = fmaf(Z.x, r.inv.z, -r.od.z), nz1 = fmaf(Z.y, r.inv.z, -r.od.z), fz0 = fmaf(Z.z, r.inv.z, -r.od.z), fz1 = fmaf(Z.w, r.inv.z, -r.od.z);

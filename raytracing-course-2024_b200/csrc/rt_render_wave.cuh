@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
 
     // box-pair step and leaf step of the lane's ray (callers predicate them)
     auto node_step = [&]() {
-        pair_step(sp, L.nodes, rs, t_best, cur, st);
+        pair_step<Space, true, IsSmem<Space>::value>(sp, L.nodes, rs, t_best, cur, st);   // shared-memory scenes always carry packed references
         if (STATS) cnt.node_tests += 2;
     };
     auto leaf_step = [&]() {
