@@ -67,6 +67,9 @@ typedef struct RtSceneInfo {
     int32_t scene_in_shared_memory;   /* 1 if the render kernels stage the whole scene in shared memory   */
     int32_t device;
     int64_t device_bytes;             /* bytes of the device-resident scene                               */
+    int32_t bvh_builder;              /* 0 = host SAH sweep (default), 1 = GPU LBVH builder (env RT_BVH_BUILDER=gpu) */
+    int32_t reserved1;
+    double  bvh_build_ms;             /* time spent building the finite-primitive BVH (create_bvh_tree, gltf_to_scene.rs:72) */
 } RtSceneInfo;
 
 typedef struct RtRenderParams {

@@ -49,7 +49,8 @@ class RtSceneDesc(C.Structure):
 
 class RtSceneInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n_tris", "n_lights", "n_materials", "n_nodes", "n_leaves", "bvh_depth", "max_leaf_size",
-                                         "bvh_validate_failures", "scene_in_shared_memory", "device")] + [("device_bytes", C.c_int64)]
+                                         "bvh_validate_failures", "scene_in_shared_memory", "device")] + [("device_bytes", C.c_int64)] + \
+               [("bvh_builder", C.c_int32), ("reserved1", C.c_int32), ("bvh_build_ms", C.c_double)]
 
 
 class RtRenderParams(C.Structure):

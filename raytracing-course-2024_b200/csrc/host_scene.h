@@ -47,6 +47,11 @@ struct BvhBuildParams {
 
 // tri_v: n x 9 doubles (load order); ids: which triangles to include (all, or the lights).
 void build_bvh(const double* tri_v, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out);
+// GPU builder (rt_bvh_gpu.cu): Morton codes + radix sort + Karras hierarchy + refit + collapse to leaves <= max_leaf_size.
+// Same output format; lower tree quality than the SAH sweep, milliseconds instead of seconds on large meshes.  Returns
+// false (with *err) when CUDA fails or the set is too small to bother (<= 2 * max_leaf_size triangles).
+bool build_bvh_gpu(const double* tri_v, int n_total_tris, const std::vector<int32_t>& ids, const BvhBuildParams& p, int device, FlatBvh* out,
+                   double* build_ms, std::string* err);
 // validate_bvh (bvh.rs:299-322) on the flattened tree: every leaf box contains its triangles' EPS-padded
 // boxes, every inner pair box contains the boxes stored in the child node.  Returns the number of violations.
 int validate_flat_bvh(const FlatBvh& bvh, const double* tri_v);

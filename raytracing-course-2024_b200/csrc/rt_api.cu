@@ -1,6 +1,7 @@
 // rt_api.cu -- implementation of the C ABI declared in include/rt_api.h: scene ingest (flatten + BVH build +
 // upload), the render entry points that replace render_scene (rendering.rs:21-69), the nearest-hit query and the
 // test/roofline helpers.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstdlib>
@@ -38,6 +39,8 @@ struct RtScene {
     std::vector<double> tri_d_host;        // BVH-ordered a, e1, e2 in f64 (precision-64 queries)
     int device = 0, sms = 0;
     int n_mats = 0, validate_failures = 0;
+    int bvh_builder = 0;                   // 0 = host SAH sweep, 1 = GPU LBVH (RT_BVH_BUILDER=gpu)
+    double bvh_build_ms = 0.0;
     uint32_t stack_entries = 16;
     bool use_smem = false;
     // device state
@@ -147,7 +150,20 @@ int flatten_scene(RtScene* s) {
     if (bp.max_leaf_size > 8) bp.max_leaf_size = 8;
     std::vector<int32_t> all((size_t)n);
     for (int i = 0; i < n; ++i) all[(size_t)i] = i;
-    rtb::build_bvh(h.tri_v.data(), all, bp, &s->bvh);
+    // builder: host SAH sweep (default: best trees) or the GPU LBVH builder (RT_BVH_BUILDER=gpu: fastest scene load)
+    const char* which = std::getenv("RT_BVH_BUILDER");
+    s->bvh_builder = 0; s->bvh_build_ms = 0.0;
+    bool built = false;
+    if (which && std::strcmp(which, "gpu") == 0 && s->device >= 0) {
+        std::string gerr;
+        built = rtb::build_bvh_gpu(h.tri_v.data(), n, all, bp, s->device, &s->bvh, &s->bvh_build_ms, &gerr);
+        if (built) s->bvh_builder = 1;
+    }
+    if (!built) {
+        const auto t0 = std::chrono::steady_clock::now();
+        rtb::build_bvh(h.tri_v.data(), all, bp, &s->bvh);
+        s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
+    }
     s->validate_failures = rtb::validate_flat_bvh(s->bvh, h.tri_v.data());
 
     // lights: emission.norm() > EPS (gltf_to_scene.rs:240)
@@ -492,6 +508,7 @@ int rt_scene_info(const RtScene* s, RtSceneInfo* o) {
     o->n_nodes = s->bvh.n_nodes; o->n_leaves = s->bvh.n_leaves; o->bvh_depth = s->bvh.depth; o->max_leaf_size = s->bvh.max_leaf;
     o->bvh_validate_failures = s->validate_failures; o->scene_in_shared_memory = s->use_smem ? 1 : 0; o->device = s->device;
     o->device_bytes = (int64_t)s->blob_host.size();
+    o->bvh_builder = s->bvh_builder; o->bvh_build_ms = s->bvh_build_ms;
     return RT_OK;
 }
 

@@ -414,3 +414,37 @@ def test_non_black_background_matches_oracle_and_both_kernels(gpu_rt, oracle):
     c, _ = black.render_linear(seed=9)
     assert _lum(b.astype(np.float64)).mean() > 1.05 * _lum(c.astype(np.float64)).mean()      # the background really contributes
     sc.close(); black.close()
+
+
+@pytest.mark.parametrize("name", ["practice7_2", "practice7_4"])
+def test_gpu_bvh_builder_gives_the_same_hits(gpu_rt, monkeypatch, name):
+    """the GPU LBVH builder (RT_BVH_BUILDER=gpu) replaces create_bvh_tree (bvh.rs:26-144).  Tree shape is
+    not observable: the flattened tree must pass validate_bvh (bvh.rs:299-322 restated) and every primary ray must
+    report the same triangle and distance as with the host SAH tree (f64 triangle tests: exact ties aside)."""
+    W = H = 256
+    host = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 16)
+    monkeypatch.setenv("RT_BVH_BUILDER", "gpu")
+    dev = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 16)
+    monkeypatch.delenv("RT_BVH_BUILDER")
+    ih, idv = host.info(), dev.info()
+    assert ih["bvh_builder"] == 0 and idv["bvh_builder"] == 1
+    assert idv["bvh_validate_failures"] == 0 and idv["max_leaf_size"] <= 4 and idv["n_tris"] == ih["n_tris"]
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H))
+    xy = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.int32)
+    rays = host.primary_rays(xy, np.full((xy.shape[0], 2), 0.5))
+    ia, ta = host.trace_primary(rays, precision=64)
+    ib, tb = dev.trace_primary(rays, precision=64)
+    same = ia == ib
+    assert same.mean() > 0.995, same.mean()
+    assert np.array_equal(ta, tb)                                       # same distance everywhere (same f64 triangle arithmetic) ...
+    assert ((ia >= 0) == (ib >= 0)).all()                               # ... so an id mismatch is an exact tie: the ray runs along an edge
+    #                                                                     shared by two triangles (the image diagonal = the back wall's diagonal)
+    # the render goes through the same tree: same path statistics and image up to FP32 tie-breaks
+    a, sa = host.render_linear(seed=4, collect_stats=True)
+    b, sb = dev.render_linear(seed=4, collect_stats=True)
+    for k in ("samples", "segments", "vertices"):
+        assert abs(sa[k] - sb[k]) <= 2e-4 * sa[k], (k, sa[k], sb[k])
+    assert abs(_lum(a.astype(np.float64)).mean() - _lum(b.astype(np.float64)).mean()) < 0.02 * _lum(a.astype(np.float64)).mean()
+    print(f"{name}: host SAH {ih['bvh_build_ms']:.1f} ms / {ih['n_nodes']} nodes / depth {ih['bvh_depth']};  GPU LBVH {idv['bvh_build_ms']:.2f} ms / "
+          f"{idv['n_nodes']} nodes / depth {idv['bvh_depth']};  box tests per segment {sa['node_tests'] / sa['segments']:.1f} vs {sb['node_tests'] / sb['segments']:.1f}")
+    host.close(); dev.close()
