@@ -284,6 +284,7 @@ int flatten_scene(RtScene* s) {
     L.total_bytes = (uint32_t)s->blob_host.size();
     L.n_nodes = s->bvh.n_nodes; L.n_tris = n; L.n_mats = s->n_mats; L.n_lights = n_lights;
     L.n_lnodes = s->light_bvh.n_nodes; L.light_bvh = use_light_bvh ? 1 : 0;
+    L.inv_n_lights = n_lights > 0 ? 1.0f / (float)n_lights : 0.0f;
 
     // entry 0 = RT_CUR_DONE, one marker per walk; the light-pdf walk runs on top of a ray's live stack (wavefront kernel)
     const int need = s->bvh.depth + 3 + (use_light_bvh ? s->light_bvh.depth + 2 : 0);
@@ -302,6 +303,7 @@ void fill_camera(const rtb::HostScene& h, rtd::Camera* c) {
     }
     c->tan_x = (float)std::tan(h.camera_fov_x * 0.5);     // rendering.rs:76
     c->tan_y = (float)std::tan(h.camera_fov_y * 0.5);     // rendering.rs:77
+    c->two_over_w = (float)(2.0 / (double)h.width); c->two_over_h = (float)(2.0 / (double)h.height);   // rendering.rs:74-75
 }
 
 int upload_scene(RtScene* s) {
@@ -365,6 +367,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     a.W = h.width; a.H = h.height; a.ray_depth = h.ray_depth;
     a.max_attempts = p->max_attempts > 0 ? p->max_attempts : 64;
     a.n_comp = s->L.n_lights > 0 ? 3 : 2;                     // rendering.rs:23-31
+    a.inv_n_comp = 1.0f / (float)a.n_comp;
     a.s_begin = s0; a.s_end = s1;
     a.tiles_x = (uint32_t)((h.width + 7) / 8);
     const uint32_t tiles_y = (uint32_t)((h.height + 3) / 4);

@@ -64,6 +64,7 @@ struct SceneLayout {
     uint32_t total_bytes;
     int32_t n_nodes, n_tris, n_mats, n_lights, n_lnodes;
     int32_t light_bvh;                           // 1: pdf walks the light BVH, 0: loops over all lights
+    float inv_n_lights;                          // 1 / n_lights (MultipleLightSamplingDistribution::pdf, distributions.rs:183)
     int32_t packed_refs;                         // 1: the x planes of `nodes` carry 16-bit child references (pair_step PACKED)
 };
 #define RT_BRUTE_LIGHTS 8
@@ -376,7 +377,7 @@ RT_DEV float light_pdf(const Space& sp, const SceneLayout& L, SmemStack& st, flo
             cur = st.pop();
         }
     }
-    return sum / (float)L.n_lights;
+    return sum * L.inv_n_lights;
 }
 
 // pdf of the cosine component (distributions.rs:65-67) and of the VNDF component (:276-297) for unit l.

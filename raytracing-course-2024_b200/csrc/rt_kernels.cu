@@ -52,8 +52,8 @@ RT_DEV Material load_material(const Space& sp, const SceneLayout& L, int id) {
 // get_ray_to_pixel (rendering.rs:71-84) with explicit jitter.
 RT_DEV void camera_ray(const Camera& c, int W, int H, int x, int y, float xi1, float xi2, float3& o, float3& d) {
     const float rx = (float)x + xi1, ry = (float)y + xi2;
-    const float px = (2.0f * rx / (float)W - 1.0f) * c.tan_x;
-    const float py = -(2.0f * ry / (float)H - 1.0f) * c.tan_y;
+    const float px = fmaf(rx, c.two_over_w, -1.0f) * c.tan_x;
+    const float py = -fmaf(ry, c.two_over_h, -1.0f) * c.tan_y;
     const float3 dir = f3(c.right[0], c.right[1], c.right[2]) * px + f3(c.up[0], c.up[1], c.up[2]) * py + f3(c.fwd[0], c.fwd[1], c.fwd[2]);
     o = f3(c.pos[0], c.pos[1], c.pos[2]);
     d = normalize(dir);
@@ -63,7 +63,7 @@ RT_DEV void camera_ray(const Camera& c, int W, int H, int x, int y, float xi1, f
 // (distributions.rs:188-192) followed by MixDistribution::pdf (:194-201).  Returns the mixture pdf; `terms` are
 // the per-direction quantities for the BRDF of the accepted direction.
 template <class Space, bool STATS>
-RT_DEV float mix_sample_and_pdf(const Space& sp, const SceneLayout& L, SmemStack& st, int n_comp, float3 P, float3 n, float3 v,
+RT_DEV float mix_sample_and_pdf(const Space& sp, const SceneLayout& L, SmemStack& st, int n_comp, float inv_n_comp, float3 P, float3 n, float3 v,
                                 float nv, float alpha, float alpha2, float g1v, uint4 rnd, float3& l, DirTerms& terms, Counters& cnt) {
     const uint32_t comp = __umulhi(rnd.x, (uint32_t)n_comp);           // gen_range(0..len)
     const float u1 = u01(rnd.y), u2 = u01(rnd.z);
@@ -73,7 +73,7 @@ RT_DEV float mix_sample_and_pdf(const Space& sp, const SceneLayout& L, SmemStack
     terms = dir_terms(n, v, l, alpha2);
     float pdf = pdf_cosine(terms.nl) + pdf_vndf(terms.d_nochi, g1v, nv);
     if (n_comp == 3) pdf += light_pdf<Space, STATS>(sp, L, st, P, l, cnt);
-    return pdf / (float)n_comp;
+    return pdf * inv_n_comp;
 }
 
 template <class Space> struct SpaceMaker;
@@ -195,7 +195,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS) render_kernel(const R
                 bool accepted = false;
                 for (int attempt = 0; attempt < a.max_attempts; ++attempt) {        // :102-110
                     const uint4 rnd = philox4x32_10(make_uint4(pix, (uint32_t)s_this, call++, RT_PHILOX_TAG), key);
-                    pdf = mix_sample_and_pdf<Space, STATS>(sp, L, st, a.n_comp, P, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
+                    pdf = mix_sample_and_pdf<Space, STATS>(sp, L, st, a.n_comp, a.inv_n_comp, P, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
                     if (STATS) ++c_attempts;
                     if (pdf > 0.0f && dot(l, ns) > 0.0f) { accepted = true; break; }
                 }
@@ -472,7 +472,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const char* blob, const Scene
         float pdf = pdf_cosine(t.nl) + pdf_vndf(t.d_nochi, ggx_g1(nv, alpha2), nv);
         const int n_comp = L.n_lights > 0 ? 3 : 2;
         if (n_comp == 3) pdf += light_pdf<GmemSpace, false>(sp, L, st, P, l, cnt);
-        y[0] = pdf / (float)n_comp;
+        y[0] = pdf * (1.0f / (float)n_comp);
     } else if (fn == RT_FN_SAMPLE_COSINE) {
         const float3 nn = f3(x[0], x[1], x[2]);
         const float3 l = sample_cosine(nn, x[3], x[4]);

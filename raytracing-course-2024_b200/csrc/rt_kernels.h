@@ -11,6 +11,7 @@ namespace rtd {
 struct Camera {
     float pos[3], right[3], up[3], fwd[3];
     float tan_x, tan_y;  // tan(fov_x/2), tan(fov_y/2) evaluated in f64 on the host (rendering.rs:76-77)
+    float two_over_w, two_over_h;  // 2/width, 2/height (rendering.rs:74-75 without a division per sample)
 };
 
 struct RenderArgs {
@@ -19,6 +20,7 @@ struct RenderArgs {
     Camera cam;
     float bg[3];
     int32_t W, H, ray_depth, max_attempts, n_comp;
+    float inv_n_comp;            // 1 / n_comp (MixDistribution::pdf, distributions.rs:194-201)
     int32_t s_begin, s_end, chunk_size, n_chunks;
     uint32_t tiles_x, n_pix_items, total_items;
     uint32_t stack_entries;

@@ -264,7 +264,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                     const float alpha = mat.roughness * mat.roughness, alpha2 = alpha * alpha;
                     const float g1v = ggx_g1(nv, alpha2);
                     float3 l; DirTerms terms;
-                    const float pdf = mix_sample_and_pdf<Space, STATS>(sp, L, st, a.n_comp, Pt, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
+                    const float pdf = mix_sample_and_pdf<Space, STATS>(sp, L, st, a.n_comp, a.inv_n_comp, Pt, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
                     ++attempt;
                     if (STATS) ++c_attempts;
                     if (pdf > 0.0f && dot(l, ns) > 0.0f) {                       // :107
