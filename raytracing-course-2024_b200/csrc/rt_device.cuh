@@ -28,6 +28,7 @@ RT_DEV float3 cross(float3 a, float3 b) { return f3(fmaf(a.y, b.z, -a.z * b.y), 
 RT_DEV float3 fma3(float3 a, float s, float3 b) { return f3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }  // a*s + b
 RT_DEV float3 normalize(float3 a) { return a * rsqrtf(dot(a, a)); }
 RT_DEV float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+RT_DEV float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // MUFU.SQRT, ~1 ulp
 RT_DEV bool finite3(float3 a) { return isfinite(a.x) && isfinite(a.y) && isfinite(a.z); }
 
 // ------------------------------------------------------------------------------------------------ Philox4x32-10
@@ -274,7 +275,7 @@ RT_DEV float ggx_g1(float nx, float alpha2) {
     if (!(nx > 0.0f)) return 0.0f;
     const float nx2 = nx * nx;
     const float tan2 = fmaxf(1.0f - nx2, 0.0f) * fast_rcp(nx2);
-    return 2.0f * fast_rcp(1.0f + sqrtf(fmaf(alpha2, tan2, 1.0f)));
+    return 2.0f * fast_rcp(1.0f + fast_sqrt(fmaf(alpha2, tan2, 1.0f)));
 }
 RT_DEV float pow5(float x) { const float x2 = x * x; return x2 * x2 * x; }
 
@@ -297,7 +298,7 @@ RT_DEV float3 brdf_eval(const Material& m, float d_chi, float g1l, float g1v, fl
 // The reference draws the sphere point from three normals; (u1,u2) -> (z, phi) is the same distribution.
 RT_DEV float3 sphere_uniform(float u1, float u2) {
     const float z = fmaf(-2.0f, u1, 1.0f);
-    const float r = sqrtf(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
+    const float r = fast_sqrt(fmaxf(0.0f, fmaf(-z, z, 1.0f)));
     float s, c;
     __sincosf(2.0f * RT_PI_F * u2, &s, &c);
     return f3(r * c, r * s, z);
@@ -320,7 +321,7 @@ RT_DEV float3 sample_vndf(float3 n, float3 v, float alpha, float u1, float u2) {
     float sn, cs;
     __sincosf(2.0f * RT_PI_F * u1, &sn, &cs);
     const float z = fmaf(1.0f - u2, 1.0f + Vh.z, -Vh.z);
-    const float r = sqrtf(fminf(fmaxf(fmaf(-z, z, 1.0f), 0.0f), 1.0f));
+    const float r = fast_sqrt(fminf(fmaxf(fmaf(-z, z, 1.0f), 0.0f), 1.0f));
     const float3 Nh = f3(fmaf(r, cs, Vh.x), fmaf(r, sn, Vh.y), z + Vh.z);
     const float3 Ne = normalize(f3(alpha * Nh.x, alpha * Nh.y, fmaxf(0.0f, Nh.z)));
     const float3 m = t1 * Ne.x + t2 * Ne.y + n * Ne.z;
