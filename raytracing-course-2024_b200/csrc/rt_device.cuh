@@ -26,7 +26,8 @@ RT_DEV float3 operator*(float3 a, float3 b) { return f3(a.x * b.x, a.y * b.y, a.
 RT_DEV float dot(float3 a, float3 b) { return fmaf(a.x, b.x, fmaf(a.y, b.y, a.z * b.z)); }
 RT_DEV float3 cross(float3 a, float3 b) { return f3(fmaf(a.y, b.z, -a.z * b.y), fmaf(a.z, b.x, -a.x * b.z), fmaf(a.x, b.y, -a.y * b.x)); }
 RT_DEV float3 fma3(float3 a, float s, float3 b) { return f3(fmaf(a.x, s, b.x), fmaf(a.y, s, b.y), fmaf(a.z, s, b.z)); }  // a*s + b
-RT_DEV float3 normalize(float3 a) { return a * rsqrtf(dot(a, a)); }
+RT_DEV float fast_rsqrt(float x) { float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // one MUFU.RSQ, no denormal rescaling
+RT_DEV float3 normalize(float3 a) { return a * fast_rsqrt(dot(a, a)); }
 RT_DEV float fast_rcp(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 RT_DEV float fast_sqrt(float x) { float r; asm("sqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }   // MUFU.SQRT, ~1 ulp
 RT_DEV bool finite3(float3 a) { return isfinite(a.x) && isfinite(a.y) && isfinite(a.z); }
