@@ -144,8 +144,10 @@ int flatten_scene(RtScene* s) {
     const rtb::HostScene& h = s->host;
     const int n = h.n_tris();
     rtb::BvhBuildParams bp;
-    bp.max_leaf_size = env_int("RT_BVH_MAX_LEAF", 4);
-    bp.traversal_cost = env_double("RT_BVH_TRAV_COST", 1.0);
+    // measured on B200 (tools/sweep.py): leaves of <= 2 triangles (tested side by side by the kernel) and a box test priced at
+    // 2 triangle tests give the fastest trees; the reference's own limit is 4 (bvh.rs:89)
+    bp.max_leaf_size = env_int("RT_BVH_MAX_LEAF", 2);
+    bp.traversal_cost = env_double("RT_BVH_TRAV_COST", 2.0);
     if (bp.max_leaf_size < 1) bp.max_leaf_size = 1;
     if (bp.max_leaf_size > 8) bp.max_leaf_size = 8;
     std::vector<int32_t> all((size_t)n);
@@ -156,7 +158,9 @@ int flatten_scene(RtScene* s) {
     bool built = false;
     if (which && std::strcmp(which, "gpu") == 0 && s->device >= 0) {
         std::string gerr;
-        built = rtb::build_bvh_gpu(h.tri_v.data(), n, all, bp, s->device, &s->bvh, &s->bvh_build_ms, &gerr);
+        rtb::BvhBuildParams gp = bp;
+        if (!std::getenv("RT_BVH_MAX_LEAF")) gp.max_leaf_size = 4;           // LBVH subtrees collapse into leaves of <= 4
+        built = rtb::build_bvh_gpu(h.tri_v.data(), n, all, gp, s->device, &s->bvh, &s->bvh_build_ms, &gerr);
         if (built) s->bvh_builder = 1;
     }
     if (!built) {
@@ -284,6 +288,7 @@ int flatten_scene(RtScene* s) {
     L.total_bytes = (uint32_t)s->blob_host.size();
     L.n_nodes = s->bvh.n_nodes; L.n_tris = n; L.n_mats = s->n_mats; L.n_lights = n_lights;
     L.n_lnodes = s->light_bvh.n_nodes; L.light_bvh = use_light_bvh ? 1 : 0;
+    L.max_leaf = s->bvh.max_leaf;
     L.inv_n_lights = n_lights > 0 ? 1.0f / (float)n_lights : 0.0f;
 
     // entry 0 = RT_CUR_DONE, one marker per walk; the light-pdf walk runs on top of a ray's live stack (wavefront kernel)

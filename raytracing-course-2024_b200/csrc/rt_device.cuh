@@ -66,6 +66,7 @@ struct SceneLayout {
     uint32_t total_bytes;
     int32_t n_nodes, n_tris, n_mats, n_lights, n_lnodes;
     int32_t light_bvh;                           // 1: pdf walks the light BVH, 0: loops over all lights
+    int32_t max_leaf;                            // largest leaf of the finite-primitive BVH (the kernel unrolls leaves of <= 2 triangles)
     float inv_n_lights;                          // 1 / n_lights (MultipleLightSamplingDistribution::pdf, distributions.rs:183)
     int32_t packed_refs;                         // 1: the x planes of `nodes` carry 16-bit child references (pair_step PACKED)
 };

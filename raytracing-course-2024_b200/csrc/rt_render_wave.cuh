@@ -81,6 +81,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
     const bool bg_nonzero = (a.bg[0] != 0.f) | (a.bg[1] != 0.f) | (a.bg[2] != 0.f);
     const size_t n_pix = (size_t)a.W * (size_t)a.H;
     const int burst_exit = a.burst_exit, node_min = a.node_min;
+    const bool small_leaves = a.L.max_leaf <= 2;
 
     Counters cnt; cnt.node_tests = 0; cnt.tri_tests = 0; cnt.light_tri_tests = 0;
     unsigned long long c_samples = 0, c_segments = 0, c_vertices = 0, c_attempts = 0, c_cap = 0, c_nonfinite = 0;
@@ -108,6 +109,18 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
         const float3 d = f3(fast_rcp(rs.inv.x), fast_rcp(rs.inv.y), fast_rcp(rs.inv.z));
         const float3 o = rs.od * d;
         const int skip_tri = pool.ldi(F_TRI, slot);
+        if (small_leaves) {                                                // leaves of 1-2 triangles: both tests side by side, one update
+            const int second = first + (n > 1 ? 1 : 0);
+            float t0, u0, v0, t1, u1, v1;
+            const bool ok0 = tri_test(o, d, load_tri_test(sp, L.tri_t, first), t0, u0, v0) && first != skip_tri;
+            const bool ok1 = tri_test(o, d, load_tri_test(sp, L.tri_t, second), t1, u1, v1) && second != skip_tri && n > 1;
+            if (STATS) cnt.tri_tests += (unsigned long long)n;
+            const bool take1 = ok1 && (!ok0 || t1 < t0);                   // strict <: the first triangle keeps exact ties (bvh.rs:269)
+            const float tw = take1 ? t1 : t0;
+            if ((ok0 || ok1) && tw < t_best) { t_best = tw; hit_tri = take1 ? second : first; pool.stf(F_U, slot, take1 ? u1 : u0); pool.stf(F_V, slot, take1 ? v1 : v0); }
+            cur = st.pop();
+            return;
+        }
         for (int i = first; i < first + n; ++i) {
             float t, u, v;
             const bool ok = tri_test(o, d, load_tri_test(sp, L.tri_t, i), t, u, v);
@@ -319,6 +332,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                     if (cur >= 0) node_step();
 #endif
 #if RT_NODE_UNROLL >= 3
+                    if (cur >= 0) node_step();
+#endif
+#if RT_NODE_UNROLL >= 4
+                    if (cur >= 0) node_step();
+#endif
+#if RT_NODE_UNROLL >= 6
+                    if (cur >= 0) node_step();
                     if (cur >= 0) node_step();
 #endif
                 }
