@@ -448,3 +448,45 @@ def test_gpu_bvh_builder_gives_the_same_hits(gpu_rt, monkeypatch, name):
     print(f"{name}: host SAH {ih['bvh_build_ms']:.1f} ms / {ih['n_nodes']} nodes / depth {ih['bvh_depth']};  GPU LBVH {idv['bvh_build_ms']:.2f} ms / "
           f"{idv['n_nodes']} nodes / depth {idv['bvh_depth']};  box tests per segment {sa['node_tests'] / sa['segments']:.1f} vs {sb['node_tests'] / sb['segments']:.1f}")
     host.close(); dev.close()
+
+
+def test_full_size_frame_properties(gpu_rt):
+    """BASELINE.json's headline frame size (3840x2160, practice7_4) at a low sample count, through size-independent
+    properties: every pixel receives exactly `spp` samples; the same seed gives identical bytes; two sample shards
+    accumulated on the device equal the single call up to FP32 summation order; no attempt cap / non-finite sample; the
+    frame's mean luminance and its 16x9 block means agree with the committed converged 64x36 oracle render (same camera,
+    `fov_x = aspect * fov_y` stretch included) within Monte-Carlo tolerance."""
+    import torch
+    W, H, spp = 3840, 2160, 8
+    sc = gpu_rt.Scene.from_gltf(scene_path("practice7_4"), W, H, spp)
+    _, st = sc.render_linear(seed=77, collect_stats=True)                # the instrumented build: counters only
+    assert st["samples"] == W * H * spp and st["attempt_cap_hits"] == 0 and st["nonfinite_samples"] == 0
+    lin, _ = sc.render_linear(seed=77)                                   # the product build (the one the shards below run)
+    assert np.isfinite(lin).all()
+    a8, _ = sc.render(seed=77)
+    b8, _ = sc.render(seed=77)
+    assert np.array_equal(a8, b8)
+    ts = torch.cuda.Stream()
+    torch.cuda.set_stream(ts)
+    acc = torch.zeros(H * W * 4, dtype=torch.float32, device="cuda")
+    for lo, hi in ((0, 3), (3, 8)):
+        sc.render_accumulate_device(acc.data_ptr(), ts.cuda_stream, seed=77, sample_begin=lo, sample_end=hi)
+    torch.cuda.synchronize()
+    a = acc.view(H, W, 4)
+    assert bool((a[..., 3] == spp).all())
+    shard = (a[..., :3] / spp).cpu().numpy()
+    err = np.abs(shard.astype(np.float64) - lin)
+    assert (err <= 2e-5 * np.abs(lin) + 1e-6).mean() > 0.999             # FP32 summation order only ...
+    assert err.max() <= 1e-5 * max(1.0, float(np.abs(lin).max()))         # ... also where large terms of both signs cancel (SURVEY.md A.1 item 3)
+    # (the instrumented and the product build are different compilations: an ulp may flip a hit, so they are not compared pixel by pixel)
+    ref, var, _ = _golden("practice7_4", 64, 36, 8192)
+    blocks = _lum(lin.astype(np.float64)).reshape(36, H // 36, 64, W // 64).mean(axis=(1, 3))     # 60x60-pixel blocks = the oracle's pixels
+    lr = _lum(ref)
+    assert abs(blocks.mean() - lr.mean()) / lr.mean() < 0.01, (blocks.mean(), lr.mean())
+    coarse_g = blocks.reshape(9, 4, 16, 4).mean(axis=(1, 3)); coarse_r = lr.reshape(9, 4, 16, 4).mean(axis=(1, 3))
+    # a 60x60 block of jittered samples covers the oracle pixel's footprint: equal in expectation.  4x4 groups of them within
+    # 2 % or 5 sigma of the Monte-Carlo noise predicted from the oracle's per-pixel variance (highlights are heavy-tailed)
+    lvar = _lum(var) * (1.0 / 8192 + 1.0 / (spp * (H // 36) * (W // 64)))
+    sigma = np.sqrt(lvar.reshape(9, 4, 16, 4).sum(axis=(1, 3))) / 16.0
+    assert np.all(np.abs(coarse_g - coarse_r) <= np.maximum(0.02 * coarse_r, 5 * sigma)), float(np.abs(coarse_g - coarse_r).max())
+    sc.close()
