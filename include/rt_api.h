@@ -141,6 +141,14 @@ int rt_render_accumulate_device(RtScene* scene, const RtRenderParams* params, fl
 /* color_to_pixel (rendering.rs:250-262) over a device accumulator: mean = rgb / count, ACES, gamma 1/2.2,
  * round, saturating u8.  rgb_dev: W*H*3 bytes on the device. */
 int rt_resolve_device(const float* accum_dev, int32_t width, int32_t height, uint8_t* rgb_dev, void* stream);
+/* One frame on n GPUs of one box from ONE process (north_star: "main.rs (device and multi-GPU orchestration)"): scenes[g]
+ * holds the same scene on device g (rt_scene_load_gltf / rt_scene_create with device = g); GPU g renders samples
+ * [g*S/n, (g+1)*S/n) of every pixel, the W*H*4 float accumulators are summed on scenes[0]'s device with one ncclReduce over
+ * NVLink (libnccl is loaded with dlopen; RT_NCCL_LIB overrides its name; without NCCL the sum uses peer copies), resolved
+ * there (color_to_pixel) and copied to rgb_out.  n = 1 is rt_render.  Same bytes as rt_render up to FP32 summation order. */
+int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtRenderParams* params, uint8_t* rgb_out, RtStats* stats);
+/* Optional: create the NCCL communicators (seconds) / enable peer access for this device list ahead of the first frame. */
+int rt_multi_init(RtScene* const* scenes, int32_t n_scenes);
 
 /* Nearest-hit query of the finite-primitive BVH for caller-supplied rays: replaces
  * interesect_with_bvh_nearest_point (bvh.rs:231-247) for n rays (rays: n x 6 doubles, origin + direction).

@@ -104,6 +104,8 @@ def lib():
         L.rt_render_linear.argtypes = [vp, C.POINTER(RtRenderParams), C.POINTER(C.c_float), C.POINTER(RtStats)]
         L.rt_render_accumulate_device.argtypes = [vp, C.POINTER(RtRenderParams), vp, vp, C.POINTER(RtStats)]
         L.rt_resolve_device.argtypes = [vp, C.c_int32, C.c_int32, vp, vp]
+        L.rt_multi_init.argtypes = [C.POINTER(vp), C.c_int32]
+        L.rt_render_multi.argtypes = [C.POINTER(vp), C.c_int32, C.POINTER(RtRenderParams), C.POINTER(C.c_uint8), C.POINTER(RtStats)]
         L.rt_trace_primary.argtypes = [vp, _dp, C.c_int64, C.c_int32, C.POINTER(C.c_int32), _dp]
         L.rt_primary_rays.argtypes = [vp, C.POINTER(C.c_int32), _dp, C.c_int64, _dp]
         L.rt_eval.argtypes = [vp, C.c_int32, C.POINTER(C.c_float), C.c_int64, C.POINTER(C.c_float)]
@@ -302,3 +304,13 @@ def dump_rendered_to_png(scene: Scene, rendered: np.ndarray, path):
     rendered = np.ascontiguousarray(rendered, dtype=np.uint8)
     H, W = rendered.shape[0], rendered.shape[1]
     _check(lib().rt_write_png(os.fsencode(path), W, H, rendered.ctypes.data_as(C.POINTER(C.c_uint8))))
+
+
+def render_multi(scenes, **kw):
+    """rt_render_multi: one frame sharded by samples over the devices the scenes live on (one process, one NCCL reduce)."""
+    W, H = scenes[0].desc_scalar("width"), scenes[0].desc_scalar("height")
+    out = np.zeros((H, W, 3), dtype=np.uint8)
+    st = RtStats()
+    arr = (C.c_void_p * len(scenes))(*[s._h.value for s in scenes])
+    _check(lib().rt_render_multi(arr, len(scenes), C.byref(_params(**kw)), out.ctypes.data_as(C.POINTER(C.c_uint8)), C.byref(st)))
+    return out, st.as_dict()

@@ -5,10 +5,10 @@
 //   * errors are reported and the exit code is non-zero (the reference panics);
 //   * the PPM is truncated, not appended to (main.rs:62-66 opens with append(true), which stacks a second image
 //     behind an existing file); set RT_PPM_APPEND=1 to get the reference behaviour;
-//   * the optional 6th argument (PNG dump, main.rs:68-72) is accepted; no PNG encoder is linked in this build,
-//     so it writes `<basename>.ppm` next to it instead and says so.
+//   * the optional 6th argument (PNG dump, main.rs:68-72) writes `<basename>.png` through rt_write_png.
 // Extra knobs are environment variables only, so the positional CLI stays drop-in:
-//   RT_SEED (Philox key, default 0), RT_DEVICE (CUDA device, default 0), RT_STATS=1 (work counters).
+//   RT_SEED (Philox key, default 0), RT_DEVICE (first CUDA device, default 0), RT_GPUS (GPUs of this box to shard the
+//   samples over: one NCCL reduce of the framebuffer at the end, default 1), RT_STATS=1 (work counters).
 #include <chrono>
 #include <cstdio>
 #include <cstdlib>
@@ -29,11 +29,19 @@ int main(int argc, char** argv) {
     const char* output_ppm = argv[5];
     const int device = (int)env_ll("RT_DEVICE", 0);
 
-    RtScene* scene = nullptr;
-    if (rt_scene_load_gltf(input_scene, width, height, samples, device, &scene) != RT_OK) {
-        std::fprintf(stderr, "error: %s\n", rt_last_error());
-        return 1;
+    int n_gpus = (int)env_ll("RT_GPUS", 1);
+    if (n_gpus < 1) n_gpus = 1;
+    std::vector<RtScene*> scenes((size_t)n_gpus, nullptr);
+    auto destroy_all = [&]() { for (RtScene* s : scenes) if (s) rt_scene_destroy(s); };
+    for (int g = 0; g < n_gpus; ++g) {                                                             // main.rs:45-47 on every device
+        if (rt_scene_load_gltf(input_scene, width, height, samples, device + g, &scenes[(size_t)g]) != RT_OK) {
+            std::fprintf(stderr, "error: %s\n", rt_last_error());
+            destroy_all();
+            return 1;
+        }
     }
+    rt_multi_init(scenes.data(), n_gpus);        // NCCL communicators are part of the set-up, like the BVH build (main.rs:45-47)
+    RtScene* scene = scenes[0];
     RtSceneInfo info;
     rt_scene_info(scene, &info);
     std::printf("Scene finite primitives: %d, light sources: %d\n", info.n_tris, info.n_lights);   // main.rs:49-53
@@ -44,31 +52,31 @@ int main(int argc, char** argv) {
     params.collect_stats = (int)env_ll("RT_STATS", 0);
     RtStats stats;
     const auto start = std::chrono::steady_clock::now();                                           // main.rs:54
-    if (rt_render(scene, &params, rendered.data(), &stats) != RT_OK) {
+    if (rt_render_multi(scenes.data(), n_gpus, &params, rendered.data(), &stats) != RT_OK) {
         std::fprintf(stderr, "error: %s\n", rt_last_error());
-        rt_scene_destroy(scene);
+        destroy_all();
         return 1;
     }
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     std::printf("Rendering took %.6fs\n", secs);                                                   // main.rs:57-58
     const double msamples = (double)width * height * samples / secs / 1e6;
-    std::printf("{\"msamples_per_s\": %.3f, \"kernel_ms\": %.3f, \"total_ms\": %.3f, \"segments\": %llu}\n", msamples, stats.kernel_ms, stats.total_ms,
-                (unsigned long long)stats.segments);
+    std::printf("{\"msamples_per_s\": %.3f, \"n_gpus\": %d, \"kernel_ms\": %.3f, \"total_ms\": %.3f, \"segments\": %llu}\n", msamples, n_gpus, stats.kernel_ms,
+                stats.total_ms, (unsigned long long)stats.segments);
     std::printf("Dumping to %s\n", output_ppm);                                                    // main.rs:59
     if (rt_write_ppm(output_ppm, width, height, rendered.data(), (int)env_ll("RT_PPM_APPEND", 0)) != RT_OK) {
         std::fprintf(stderr, "error: %s\n", rt_last_error());
-        rt_scene_destroy(scene);
+        destroy_all();
         return 1;
     }
     if (argc > 6) {                                                                                // main.rs:68-72
         const std::string png = std::string(argv[6]) + ".png";
         if (rt_write_png(png.c_str(), width, height, rendered.data()) != RT_OK) {
             std::fprintf(stderr, "error: %s\n", rt_last_error());
-            rt_scene_destroy(scene);
+            destroy_all();
             return 1;
         }
         std::printf("Image dumped to %s\n", png.c_str());
     }
-    rt_scene_destroy(scene);
+    destroy_all();
     return 0;
 }

@@ -1,6 +1,8 @@
 // rt_api.cu -- implementation of the C ABI declared in include/rt_api.h: scene ingest (flatten + BVH build +
 // upload), the render entry points that replace render_scene (rendering.rs:21-69), the nearest-hit query and the
 // test/roofline helpers.  No CPU fallback: every compute entry point needs a CUDA device.
+#include <dlfcn.h>
+
 #include <chrono>
 #include <cmath>
 #include <cstdio>
@@ -614,6 +616,191 @@ int rt_render_accumulate_device(RtScene* s, const RtRenderParams* p, float* accu
         float k = 0;
         cudaEventElapsedTime(&k, s->ev[0], s->ev[2]);
         st->kernel_ms = k; st->total_ms = k;
+    }
+    return RT_OK;
+}
+
+// ---- single-process multi-GPU orchestration (north_star: main.rs device and multi-GPU orchestration) -------------------
+// NCCL is reached through dlopen so that the library has no link-time dependency on a particular libnccl (a Python host
+// usually carries its own); when it cannot be loaded the framebuffers are summed with peer copies instead.
+namespace {
+struct NcclApi {
+    void* handle = nullptr;
+    int (*CommInitAll)(void**, int, const int*) = nullptr;
+    int (*CommDestroy)(void*) = nullptr;
+    int (*GroupStart)() = nullptr;
+    int (*GroupEnd)() = nullptr;
+    int (*Reduce)(const void*, void*, size_t, int, int, int, void*, cudaStream_t) = nullptr;
+    const char* (*GetErrorString)(int) = nullptr;
+    bool ok = false;
+};
+NcclApi& nccl_api() {
+    static NcclApi api;
+    static bool tried = false;
+    if (tried) return api;
+    tried = true;
+    const char* override_path = std::getenv("RT_NCCL_LIB");
+    const char* names[] = {override_path, "libnccl.so.2", "libnccl.so"};
+    for (const char* nm : names) {
+        if (!nm || !*nm) continue;
+        api.handle = dlopen(nm, RTLD_NOW | RTLD_LOCAL);
+        if (api.handle) break;
+    }
+    if (!api.handle) return api;
+    api.CommInitAll = (int (*)(void**, int, const int*))dlsym(api.handle, "ncclCommInitAll");
+    api.CommDestroy = (int (*)(void*))dlsym(api.handle, "ncclCommDestroy");
+    api.GroupStart = (int (*)())dlsym(api.handle, "ncclGroupStart");
+    api.GroupEnd = (int (*)())dlsym(api.handle, "ncclGroupEnd");
+    api.Reduce = (int (*)(const void*, void*, size_t, int, int, int, void*, cudaStream_t))dlsym(api.handle, "ncclReduce");
+    api.GetErrorString = (const char* (*)(int))dlsym(api.handle, "ncclGetErrorString");
+    api.ok = api.CommInitAll && api.CommDestroy && api.GroupStart && api.GroupEnd && api.Reduce;
+    return api;
+}
+struct CommCache { std::vector<int> devs; std::vector<void*> comms; };
+CommCache& comm_cache() { static CommCache c; return c; }
+const int kNcclFloat32 = 7, kNcclSum = 0;     // nccl.h: ncclFloat32 = 7, ncclSum = 0 (stable since NCCL 2.0)
+}  // namespace
+
+namespace {
+// Creates (or reuses) the NCCL communicators of this device list; false when NCCL is unavailable or switched off.
+bool ensure_comms(const std::vector<int>& devs) {
+    NcclApi& nc = nccl_api();
+    if (!nc.ok || env_int("RT_NO_NCCL", 0)) return false;
+    CommCache& cc = comm_cache();
+    if (cc.devs == devs) return true;
+    for (void* c : cc.comms) nc.CommDestroy(c);
+    cc.comms.assign(devs.size(), nullptr); cc.devs.clear();
+    if (nc.CommInitAll(cc.comms.data(), (int)devs.size(), devs.data()) != 0) { cc.comms.clear(); return false; }
+    cc.devs = devs;
+    return true;
+}
+}  // namespace
+
+int rt_multi_init(RtScene* const* scenes, int32_t n) {
+    if (!scenes || n < 1) return fail(RT_ERR_INVALID, "bad argument");
+    std::vector<int> devs;
+    for (int g = 0; g < n; ++g) { if (!scenes[g] || !scenes[g]->blob_dev) return fail(RT_ERR_CUDA, "rt_multi_init: every scene must live on a CUDA device"); devs.push_back(scenes[g]->device); }
+    if (n > 1 && ensure_comms(devs)) {                      // first collective = connection set-up: do it now, on a few floats
+        NcclApi& nc = nccl_api();
+        CommCache& cc = comm_cache();
+        for (int g = 0; g < n; ++g) {
+            CUDA_TRY(cudaSetDevice(devs[(size_t)g]));
+            const int rc = ensure(&scenes[g]->accum, &scenes[g]->accum_cap, 256);
+            if (rc != RT_OK) return rc;
+            CUDA_TRY(cudaMemsetAsync(scenes[g]->accum, 0, 256 * sizeof(float4), scenes[g]->stream));
+        }
+        int rc = nc.GroupStart();
+        for (int g = 0; g < n && rc == 0; ++g) rc = nc.Reduce(scenes[g]->accum, scenes[0]->accum, 1024, kNcclFloat32, kNcclSum, 0, cc.comms[(size_t)g], scenes[g]->stream);
+        const int rc2 = nc.GroupEnd();
+        if (rc != 0 || rc2 != 0) return fail(RT_ERR_CUDA, "rt_multi_init: ncclReduce warm-up failed");
+        for (int g = 0; g < n; ++g) { CUDA_TRY(cudaSetDevice(devs[(size_t)g])); CUDA_TRY(cudaStreamSynchronize(scenes[g]->stream)); }
+    } else if (n > 1) {                                     // no NCCL: make the peer copies direct
+        for (int g = 1; g < n; ++g) {
+            int can = 0;
+            cudaDeviceCanAccessPeer(&can, devs[0], devs[(size_t)g]);
+            if (can) { cudaSetDevice(devs[0]); cudaError_t e = cudaDeviceEnablePeerAccess(devs[(size_t)g], 0); if (e != cudaSuccess) cudaGetLastError(); }
+        }
+    }
+    return RT_OK;
+}
+
+int rt_render_multi(RtScene* const* scenes, int32_t n, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st) {
+    if (!scenes || n < 1 || !rgb_out) return fail(RT_ERR_INVALID, "bad argument");
+    if (n == 1) return rt_render(scenes[0], p, rgb_out, st);
+    RtScene* s0 = scenes[0];
+    if (!s0) return fail(RT_ERR_INVALID, "null scene");
+    const int W = s0->host.width, H = s0->host.height, S = s0->host.samples;
+    const size_t n_pix = (size_t)W * (size_t)H;
+    std::vector<int> devs((size_t)n);
+    for (int g = 0; g < n; ++g) {
+        RtScene* s = scenes[g];
+        if (!s || !s->blob_dev) return fail(RT_ERR_CUDA, "rt_render_multi: every scene must live on a CUDA device");
+        if (s->host.width != W || s->host.height != H || s->host.samples != S || s->host.n_tris() != s0->host.n_tris())
+            return fail(RT_ERR_INVALID, "rt_render_multi: the scenes must describe the same frame");
+        devs[(size_t)g] = s->device;
+        for (int k = 0; k < g; ++k) if (devs[(size_t)k] == s->device) return fail(RT_ERR_INVALID, "rt_render_multi: one scene per device");
+    }
+    RtRenderParams base;
+    std::memset(&base, 0, sizeof(base));
+    if (p) base = *p;
+    int s_lo = base.sample_begin, s_hi = base.sample_end;
+    if (s_lo == 0 && s_hi == 0) s_hi = S;
+    if (s_lo < 0 || s_hi > S || s_lo >= s_hi) return fail(RT_ERR_INVALID, "sample range must satisfy 0 <= begin < end <= samples");
+    // 1. every device renders its sample shard into its own accumulator (launches are asynchronous: the GPUs run together)
+    std::vector<RenderPlan> plans((size_t)n);
+    std::vector<rtd::KernelInfo> kis((size_t)n);
+    std::vector<char> active((size_t)n, 0);
+    CUDA_TRY(cudaSetDevice(s0->device));
+    CUDA_TRY(cudaEventRecord(s0->ev[0], s0->stream));
+    for (int g = 0; g < n; ++g) {
+        RtScene* s = scenes[g];
+        CUDA_TRY(cudaSetDevice(s->device));
+        int rc = ensure(&s->accum, &s->accum_cap, n_pix);
+        if (rc != RT_OK) return rc;
+        const long long span = s_hi - s_lo;
+        RtRenderParams q = base;
+        q.sample_begin = s_lo + (int)(span * g / n); q.sample_end = s_lo + (int)(span * (g + 1) / n);   // multigpu.shard_range
+        if (q.sample_end > q.sample_begin) {
+            rc = render_to_layers(s, &q, s->stream, &plans[(size_t)g], &kis[(size_t)g]);
+            if (rc != RT_OK) return rc;
+            CUDA_TRY(rtd::launch_sum_layers(s->layers, plans[(size_t)g].args.n_chunks, n_pix, s->accum, false, s->stream));
+            active[(size_t)g] = 1;
+        } else {
+            CUDA_TRY(cudaMemsetAsync(s->accum, 0, n_pix * sizeof(float4), s->stream));
+        }
+    }
+    // 2. ONE reduce(sum) of the W*H*4 accumulators to device 0 (NVLink), the only communication of the frame
+    NcclApi& nc = nccl_api();
+    bool reduced = false;
+    if (ensure_comms(devs)) {
+        CommCache& cc = comm_cache();
+        int rc = nc.GroupStart();
+        for (int g = 0; g < n && rc == 0; ++g)
+            rc = nc.Reduce(scenes[g]->accum, s0->accum, n_pix * 4, kNcclFloat32, kNcclSum, 0, cc.comms[(size_t)g], scenes[g]->stream);
+        const int rc2 = nc.GroupEnd();
+        if (rc != 0 || rc2 != 0) return fail(RT_ERR_CUDA, std::string("ncclReduce: ") + (nc.GetErrorString ? nc.GetErrorString(rc ? rc : rc2) : "error"));
+        reduced = true;
+    }
+    if (!reduced) {                                   // peer copies into device 0's (now free) layer buffer + sum
+        for (int g = 1; g < n; ++g) {
+            RtScene* s = scenes[g];
+            CUDA_TRY(cudaSetDevice(s->device));
+            CUDA_TRY(cudaEventRecord(s->ev[3], s->stream));
+            CUDA_TRY(cudaSetDevice(s0->device));
+            CUDA_TRY(cudaStreamWaitEvent(s0->stream, s->ev[3], 0));
+            int rc = ensure(&s0->layers, &s0->layers_cap, n_pix);
+            if (rc != RT_OK) return rc;
+            CUDA_TRY(cudaMemcpyPeerAsync(s0->layers, s0->device, s->accum, s->device, n_pix * sizeof(float4), s0->stream));
+            CUDA_TRY(rtd::launch_sum_layers(s0->layers, 1, n_pix, s0->accum, true, s0->stream));
+        }
+    }
+    // 3. device 0 resolves (color_to_pixel) and returns the bytes
+    CUDA_TRY(cudaSetDevice(s0->device));
+    int rc = ensure(&s0->rgb_dev, &s0->rgb_cap, n_pix * 3);
+    if (rc != RT_OK) return rc;
+    CUDA_TRY(rtd::launch_resolve_u8(s0->accum, n_pix, s0->rgb_dev, s0->stream));
+    CUDA_TRY(cudaEventRecord(s0->ev[2], s0->stream));
+    CUDA_TRY(cudaMemcpyAsync(rgb_out, s0->rgb_dev, n_pix * 3, cudaMemcpyDeviceToHost, s0->stream));
+    CUDA_TRY(cudaEventRecord(s0->ev[3], s0->stream));
+    for (int g = n - 1; g >= 0; --g) { CUDA_TRY(cudaSetDevice(scenes[g]->device)); CUDA_TRY(cudaStreamSynchronize(scenes[g]->stream)); }
+    if (st) {
+        RtStats total; std::memset(&total, 0, sizeof(total));
+        for (int g = 0; g < n; ++g) {
+            if (!active[(size_t)g]) continue;
+            RtStats one;
+            CUDA_TRY(cudaSetDevice(scenes[g]->device));
+            if ((rc = collect_stats(scenes[g], plans[(size_t)g], kis[(size_t)g], &one, 2, scenes[g]->stream)) != RT_OK) return rc;
+            const uint64_t* a = &one.samples; uint64_t* b = &total.samples;
+            for (int k = 0; k < 10; ++k) b[k] += a[k];                       // the ten uint64 counters
+            total.kernel = one.kernel; total.block_threads = one.block_threads; total.blocks_per_sm = one.blocks_per_sm; total.grid_blocks = one.grid_blocks;
+            total.regs_per_thread = one.regs_per_thread; total.smem_bytes_per_block = one.smem_bytes_per_block; total.scene_in_shared_memory = one.scene_in_shared_memory;
+        }
+        total.kernel_launches += 2;                                           // resolve + (reduce or sum)
+        float k = 0, t = 0;
+        CUDA_TRY(cudaSetDevice(s0->device));
+        cudaEventElapsedTime(&k, s0->ev[0], s0->ev[2]); cudaEventElapsedTime(&t, s0->ev[0], s0->ev[3]);
+        total.kernel_ms = k; total.total_ms = t;
+        *st = total;
     }
     return RT_OK;
 }

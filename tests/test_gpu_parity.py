@@ -490,3 +490,32 @@ def test_full_size_frame_properties(gpu_rt):
     sigma = np.sqrt(lvar.reshape(9, 4, 16, 4).sum(axis=(1, 3))) / 16.0
     assert np.all(np.abs(coarse_g - coarse_r) <= np.maximum(0.02 * coarse_r, 5 * sigma)), float(np.abs(coarse_g - coarse_r).max())
     sc.close()
+
+
+def test_single_process_multi_gpu_render(gpu_rt, monkeypatch, tmp_path):
+    """rt_render_multi (8e; north_star 'main.rs (device and multi-GPU orchestration)'): samples sharded over the GPUs of the
+    box from one process, ONE reduce of the framebuffer (NCCL through dlopen, or peer copies with RT_NO_NCCL=1), resolve
+    on device 0.  Same image as the single-GPU call up to FP32 summation order; needs >= 2 GPUs."""
+    if gpu_rt.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    n = min(gpu_rt.device_count(), 4)
+    W, H, spp = 256, 144, 66
+    scenes = [gpu_rt.Scene.from_gltf(scene_path("practice7_4"), W, H, spp, device=g) for g in range(n)]
+    one, st1 = scenes[0].render(seed=5, collect_stats=True)
+    for no_nccl in ("0", "1"):
+        monkeypatch.setenv("RT_NO_NCCL", no_nccl)
+        multi, stn = gpu_rt.render_multi(scenes, seed=5, collect_stats=True)
+        assert stn["samples"] == W * H * spp == st1["samples"]
+        assert abs(stn["segments"] - st1["segments"]) <= 1e-4 * st1["segments"]
+        d = np.abs(multi.astype(int) - one.astype(int))
+        assert d.max() <= 1 and (d > 0).mean() < 0.01, (no_nccl, int(d.max()), float((d > 0).mean()))
+    monkeypatch.delenv("RT_NO_NCCL")
+    out = tmp_path / "m.ppm"
+    env = dict(os.environ, RT_GPUS=str(n), RT_SEED="5")
+    r = subprocess.run([gpu_rt.CLI_PATH, scene_path("practice7_4"), str(W), str(H), str(spp), str(out)], capture_output=True, text=True, env=env)
+    assert r.returncode == 0, r.stderr
+    hdr = f"P6\n{W} {H}\n255\n".encode()
+    cli = np.frombuffer(out.read_bytes()[len(hdr):], dtype=np.uint8).reshape(H, W, 3)
+    assert np.abs(cli.astype(int) - one.astype(int)).max() <= 1
+    for s in scenes:
+        s.close()
