@@ -1,8 +1,9 @@
-// rt_kernels.cu -- the sm_100a kernels: the persistent per-lane path tracer that replaces the pixel loop of
-// render_scene (rendering.rs:21-69), plus the nearest-hit query kernel, the resolve (color_to_pixel) kernels,
-// the unit-function kernel used by the parity tests and the FFMA issue micro-benchmark.
+// rt_kernels.cu -- the sm_100a kernels that replace the pixel loop of render_scene (rendering.rs:21-69): the shading
+// helpers shared by both render kernels, v1 (`render_kernel`, the per-lane megakernel kept as the A/B baseline), v3
+// (`render_wave_kernel`, rt_render_wave.cuh: the product path), plus the nearest-hit query kernel, the resolve
+// (color_to_pixel) kernels, the unit-function kernel used by the parity tests and the FFMA issue micro-benchmark.
 //
-// Design (DESIGN.md has the full story):
+// v1 design (DESIGN.md has the full story, rt_render_wave.cuh the v3 one):
 //   * one persistent grid, CTAs = SMs x occupancy; every LANE owns one (pixel, sample-chunk) work item at a time
 //     and pulls the next one from a global counter (warp-aggregated atomic) the moment it runs out of samples, so
 //     there is no per-warp tail; inside an item the lane regenerates a camera path as soon as its path ends;

@@ -1,23 +1,26 @@
-// rt_render_wave.cuh -- render kernel v3: the warp-local wavefront with burst traversal.  Included by rt_kernels.cu
-// after the shading helpers (DirTerms, mix_sample_and_pdf, camera_ray, load_material, SpaceMaker, IsSmem).
+// rt_render_wave.cuh -- render kernel v3 (the product path): the warp-local wavefront with burst traversal.  Included by
+// rt_kernels.cu after the shading helpers (DirTerms, mix_sample_and_pdf, camera_ray, load_material, SpaceMaker, IsSmem).
 //
 // ncu of v1 (profiles/r1_v1_*): 31 % warp execution efficiency -- the node loop issues 45 % of all instructions at
 // 8.3/32 active lanes, the leaf loop 17 % at 10.3/32 and shading 38 % at ~10/32, because every lane owns ONE path and
-// the warp waits for its slowest ray / its unluckiest rejection in every iteration.  v2 (a pool whose queues were
-// serviced after EVERY traversal step, profiles/r1_v2b_*) reached 17.7/32 lanes but doubled the thread-instruction
-// count with ballots and queue arithmetic.  v3 keeps the pool and moves the bookkeeping out of the inner loop:
-//   * every warp owns a POOL of 64 path slots in shared memory (SoA, 21 words per slot) and two ring queues over them:
-//     TQ (slots holding a ray to trace) and SQ (slots waiting for shading);
-//   * TRACE BURST: the 32 lanes hold 32 rays in registers and run a plain while-while traversal; after every leaf
-//     phase ONE ballot counts the lanes whose ray is finished, and the burst ends when that count reaches
-//     `burst_exit`.  Finished lanes write (triangle, u, v) to their slot, push it on SQ and pop the next ray of TQ;
+// the warp waits for its slowest ray / its unluckiest rejection in every iteration.  A first pool whose queues were
+// serviced after EVERY traversal step reached 17.7/32 lanes but doubled the thread-instruction count with ballots and
+// queue arithmetic.  v3 keeps the pool and moves the bookkeeping out of the inner loop:
+//   * every warp owns a POOL of 64 path slots in shared memory (32-bit SoA, 22 words per slot) and two ring queues over
+//     them: TQ (slots holding a ray to trace) and SQ (slots waiting for shading) -- warp-synchronous, no atomics;
+//   * TRACE BURST: the 32 lanes hold 32 rays (only what the box tests need stays in registers).  MODE 1 (default, phased):
+//     box-pair steps run, three per vote, while at least `node_min` lanes want one; otherwise the lanes sitting on a leaf
+//     test its triangles (leaves of <= 2 triangles side by side); the burst ends when `burst_exit` lanes are finished.
+//     MODE 0: plain while-while with the same exit rule.  Finished lanes write (triangle, u, v) to their slot, push it on
+//     SQ and pop the next ray of TQ;
 //   * SHADE ROUND: whenever TQ cannot feed the idle lanes, 32 slots of SQ are shaded with all 32 lanes busy (the
-//     in-flight traversals of the other slots stay in registers): finished items are stored and replaced, ended
-//     paths regenerated, and every hit makes exactly ONE attempt of the reference's rejection loop
-//     (rendering.rs:102-110); accepted directions go to TQ, rejected slots return to SQ and retry in a later round.
-//     With 64 slots and 32 lanes, an empty TQ implies >= 32 slots on SQ, so rounds are always full until the frame's
-//     work counter runs dry.
-// Same estimator, same Philox counters (pixel, sample, call#) as v1 -> same image.
+//     in-flight traversals of the other slots stay in registers): emission / depth bookkeeping, finished items stored
+//     exactly once and replaced from the frame's work counter, then ONE Philox call per live slot -- the camera jitter of a
+//     new path or the next attempt of the reference's rejection loop (rendering.rs:102-110) -- and the camera ray or one
+//     attempt; accepted directions go to TQ, rejected slots return to SQ and retry in a later round (nobody waits).
+//     With 64 slots and 32 lanes, an empty TQ implies >= 32 slots on SQ, so rounds are full until the work counter runs dry.
+// Same estimator, same Philox counters (pixel, sample, call#) as v1 -> same image (test_kernel_variants_render_the_same_image).
+// ncu of this kernel (profiles/r1_v3d_*): 19.5/32 lanes per instruction, issue slots 75 % busy, shared-memory pipe 76 %.
 #pragma once
 
 #define RT_POOL_SLOTS 64
