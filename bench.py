@@ -147,6 +147,15 @@ def run_reference(args, rank):
     print(json.dumps(line), flush=True)
 
 
+def smem_roofline(counts, samples, kern_ms, clk):
+    per_sample = counts["node_tests"] / 2 * 48.0 + counts["tri_tests"] * 48.0 + counts["attempts"] * 144.0 + counts["segments"] * 216.0
+    mhz = (clk or {}).get("sm_mhz") or 1965.0
+    peak = 148 * 128.0 * mhz * 1e6 / 1e12
+    ach = per_sample * samples / (kern_ms * 1e-3) / 1e12
+    return {"algorithmic_bytes_per_sample": per_sample, "achieved_tbs": ach, "peak_tbs": peak, "frac": ach / peak,
+            "note": "ncu: the pipe is ~84 % busy at this rate (bank conflicts and partially filled wavefronts cost 2.6x the algorithmic bytes)"}
+
+
 def kernel_name(st):
     space = "SmemSpace" if st["scene_in_shared_memory"] else "GmemSpace"
     if st["kernel"] == 1:
@@ -324,7 +333,11 @@ def main():
                          "flop_constants": {"node": C_NODE, "tri": C_TRI, "attempt": C_ATTEMPT, "shade": C_SHADE},
                          "hbm_algorithmic_bytes": hbm_bytes, "hbm_achieved_gbs": hbm_bytes / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
                          "hbm_frac": (hbm_bytes / (kern_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
-                         "mrays_per_s": counts["segments"] * total_samples * frac_samples / (kern_ms * 1e-3) / 1e6},
+                         "mrays_per_s": counts["segments"] * total_samples * frac_samples / (kern_ms * 1e-3) / 1e6,
+                         # the resource ncu shows closest to saturation (profiles/): the shared-memory data pipe.  Algorithmic bytes per
+                         # sample = box-pair steps x 48 B + triangle tests x 48 B + 144 B of per-triangle shading data per attempt + 216 B of
+                         # slot / stack state per segment; peak = SMs x 128 B/clk x the SM clock seen during the run
+                         "smem": smem_roofline(counts, total_samples * frac_samples, kern_ms, clk)},
             "cpu_baseline": cpu,
         }
         print(json.dumps(line), flush=True)
