@@ -6,7 +6,7 @@
 // the warp waits for its slowest ray / its unluckiest rejection in every iteration.  A first pool whose queues were
 // serviced after EVERY traversal step reached 17.7/32 lanes but doubled the thread-instruction count with ballots and
 // queue arithmetic.  v3 keeps the pool and moves the bookkeeping out of the inner loop:
-//   * every warp owns a POOL of 64 path slots in shared memory (32-bit SoA, 22 words per slot) and two ring queues over
+//   * every warp owns a POOL of 64 path slots in shared memory (32-bit SoA, 19 words per slot) and two ring queues over
 //     them: TQ (slots holding a ray to trace) and SQ (slots waiting for shading) -- warp-synchronous, no atomics;
 //   * TRACE BURST: the 32 lanes hold 32 rays (only what the box tests need stays in registers).  MODE 1 (default, phased):
 //     box-pair steps run, three per vote, while at least `node_min` lanes want one; otherwise the lanes sitting on a leaf
@@ -29,12 +29,12 @@
 #endif
 // Slot fields (words, SoA [field][slot]).  A slot is read by the shade round and by the lane that traces its ray, never
 // by both at once, so hand-over fields share storage:
-//   shade -> trace: O (ray origin), D (direction), IV (safe reciprocal direction), F_TRI = triangle to skip (or -1)
-//   trace -> shade: F_TRI = nearest triangle (or -1), (F_U, F_V) = its barycentrics; D is still the ray direction
+//   shade -> trace: O (ray origin), IV (safe reciprocal direction), F_TRI = triangle to skip (or -1)
+//   trace -> shade: F_TRI = nearest triangle (or -1), (F_U, F_V) = its barycentrics; IV still gives the ray direction
 // While a ray is in flight its lane keeps only (1/d, o/d, octant offsets, best t, best triangle, node, stack pointer) in
-// registers -- they must survive the shade rounds the warp runs for OTHER slots -- and re-reads O, D and the skip
-// triangle from the slot whenever it reaches a leaf.
-enum { F_OX = 0, F_OY, F_OZ, F_DX, F_DY, F_DZ, F_IX, F_IY, F_IZ, F_TRI, F_U, F_V, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ, F_PIX, F_S, F_CHUNK, F_META, NF };
+// registers -- they must survive the shade rounds the warp runs for OTHER slots -- rebuilds origin and direction from
+// them at a leaf and re-reads only the skip triangle from the slot.
+enum { F_OX = 0, F_OY, F_OZ, F_IX, F_IY, F_IZ, F_TRI, F_U, F_V, F_TX, F_TY, F_TZ, F_AX, F_AY, F_AZ, F_PIX, F_S, F_CHUNK, F_META, NF };
 #define RT_POOL_QUEUE_BYTES (2u * RT_POOL_SLOTS)                       /* TQ and SQ: one byte per entry */
 #define RT_POOL_WARP_BYTES (RT_POOL_SLOTS * NF * 4u + RT_POOL_QUEUE_BYTES)
 enum { ST_NEED_ITEM = 0, ST_ENDED = 1, ST_GEN = 2, ST_TRACE = 3, ST_RETRY = 4, ST_EXHAUSTED = 5, ST_NONE = 6 };
@@ -266,7 +266,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 } else if (live) {
                     const uint32_t o16 = (uint32_t)tri * 16u;
                     const Material mat = load_material(sp, L, mat_id);
-                    const float3 din = pool.ld3(F_DX, s);
+                    const float3 iv = pool.ld3(F_IX, s);                          // the ray direction is not stored: d = 1 / (1/d) (2^-22, shared-memory bound)
+                    const float3 din = f3(fast_rcp(iv.x), fast_rcp(iv.y), fast_rcp(iv.z));
                     const float hu = pool.ldf(F_U, s), hv = pool.ldf(F_V, s);
                     const float3 ng = f3(sp.ld4(L.sh_ng + o16));
                     const float sgn = dot(ng, din) < 0.0f ? 1.0f : -1.0f;         // geometry.rs:115-126
@@ -297,7 +298,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                     }
                 }
                 if (accepted) {
-                    pool.st3(F_OX, s, ro); pool.st3(F_DX, s, rd); pool.st3(F_IX, s, safe_inv_dir(rd)); pool.st3(F_TX, s, T);
+                    pool.st3(F_OX, s, ro); pool.st3(F_IX, s, safe_inv_dir(rd)); pool.st3(F_TX, s, T);
                     pool.sti(F_TRI, s, skip);
                     state = ST_TRACE;
                 }
