@@ -80,7 +80,9 @@ typedef struct RtRenderParams {
     int32_t kernel_variant;           /* 0 = auto; else 10*kernel + placement (benchmarks / A-B tests):
                                          kernel 1 = per-lane megakernel, 2 / 3 = warp-local wavefront with while-while / phased trace bursts;
                                          placement 1 = scene in global memory, 2 = scene in shared memory   */
-    int32_t reserved[3];
+    int32_t tile_shard_index;         /* with tile_shard_count > 1: render only the 8x4-pixel tiles t with t % count == index  */
+    int32_t tile_shard_count;         /* (interleaved tile sharding, the multi-GPU fallback when samples < GPUs); 0 / 1 = whole frame */
+    int32_t reserved;
 } RtRenderParams;
 
 typedef struct RtStats {

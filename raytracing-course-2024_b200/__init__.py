@@ -55,7 +55,8 @@ class RtSceneInfo(C.Structure):
 
 class RtRenderParams(C.Structure):
     _fields_ = [("seed", C.c_uint64), ("sample_begin", C.c_int32), ("sample_end", C.c_int32), ("max_attempts", C.c_int32),
-                ("collect_stats", C.c_int32), ("kernel_variant", C.c_int32), ("reserved", C.c_int32 * 3)]
+                ("collect_stats", C.c_int32), ("kernel_variant", C.c_int32), ("tile_shard_index", C.c_int32), ("tile_shard_count", C.c_int32),
+                ("reserved", C.c_int32)]
 
 
 class RtStats(C.Structure):
@@ -128,10 +129,11 @@ def device_count() -> int:
     return int(n.value) if rc == RT_OK else 0
 
 
-def _params(seed=0, sample_begin=0, sample_end=0, max_attempts=0, collect_stats=False, kernel_variant=0):
+def _params(seed=0, sample_begin=0, sample_end=0, max_attempts=0, collect_stats=False, kernel_variant=0, tile_shard=(0, 0)):
     p = RtRenderParams()
     p.seed, p.sample_begin, p.sample_end = seed, sample_begin, sample_end
     p.max_attempts, p.collect_stats, p.kernel_variant = max_attempts, 1 if collect_stats else 0, kernel_variant
+    p.tile_shard_index, p.tile_shard_count = tile_shard
     return p
 
 

@@ -380,6 +380,9 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     const uint32_t tiles_y = (uint32_t)((h.height + 3) / 4);
     a.n_pix_items = a.tiles_x * tiles_y * 32u;
     a.stack_entries = s->stack_entries;
+    a.shard_count = p->tile_shard_count > 1 ? (uint32_t)p->tile_shard_count : 1u;
+    a.shard_index = a.shard_count > 1 ? (uint32_t)p->tile_shard_index : 0u;
+    if (p->tile_shard_count > 1 && (p->tile_shard_index < 0 || p->tile_shard_index >= p->tile_shard_count)) return fail(RT_ERR_INVALID, "tile_shard_index must be in [0, tile_shard_count)");
     a.node_min = std::min(32, std::max(1, env_int("RT_NODE_MIN", 8)));
     a.burst_exit = std::min(32, std::max(1, env_int("RT_BURST_EXIT", 12)));
     a.seed_lo = (uint32_t)(p->seed & 0xffffffffu); a.seed_hi = (uint32_t)(p->seed >> 32);
@@ -416,6 +419,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     int rc = ensure(&s->layers, &s->layers_cap, n_pix * (size_t)a.n_chunks);
     if (rc != RT_OK) return rc;
     a.layers = s->layers; a.work_counter = s->work_counter; a.stats = s->stats_dev;
+    if (a.shard_count > 1) CUDA_TRY(cudaMemsetAsync(s->layers, 0, n_pix * (size_t)a.n_chunks * sizeof(float4), stream));   // tiles of other shards stay zero
     CUDA_TRY(cudaMemsetAsync(s->work_counter, 0, sizeof(unsigned int), stream));
     if (plan->stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, sizeof(unsigned long long) * rtd::RT_N_STATS, stream));
     CUDA_TRY(rtd::launch_render(a, plan->variant, plan->cfg, plan->use_smem, plan->stats, s->sms, stream, ki));
@@ -436,7 +440,16 @@ int collect_stats(RtScene* s, const RenderPlan& plan, const rtd::KernelInfo& ki,
         st->attempts = v[rtd::RT_STAT_ATTEMPTS]; st->node_tests = v[rtd::RT_STAT_NODE_TESTS]; st->tri_tests = v[rtd::RT_STAT_TRI_TESTS];
         st->light_tri_tests = v[rtd::RT_STAT_LIGHT_TRI_TESTS]; st->attempt_cap_hits = v[rtd::RT_STAT_CAP_HITS]; st->nonfinite_samples = v[rtd::RT_STAT_NONFINITE];
     } else {
-        st->samples = (uint64_t)s->host.width * (uint64_t)s->host.height * (uint64_t)(plan.args.s_end - plan.args.s_begin);
+        uint64_t pixels = (uint64_t)s->host.width * (uint64_t)s->host.height;
+        if (plan.args.shard_count > 1) {                    // pixels of the 8x4 tiles t with t % count == index
+            pixels = 0;
+            const uint32_t tx_n = plan.args.tiles_x, ty_n = (uint32_t)((s->host.height + 3) / 4);
+            for (uint32_t t = plan.args.shard_index; t < tx_n * ty_n; t += plan.args.shard_count) {
+                const uint32_t ty = t / tx_n, tx = t - ty * tx_n;
+                pixels += (uint64_t)std::min(8, s->host.width - (int)tx * 8) * (uint64_t)std::min(4, s->host.height - (int)ty * 4);
+            }
+        }
+        st->samples = pixels * (uint64_t)(plan.args.s_end - plan.args.s_begin);
     }
     return RT_OK;
 }
@@ -739,7 +752,12 @@ int rt_render_multi(RtScene* const* scenes, int32_t n, const RtRenderParams* p, 
         if (rc != RT_OK) return rc;
         const long long span = s_hi - s_lo;
         RtRenderParams q = base;
-        q.sample_begin = s_lo + (int)(span * g / n); q.sample_end = s_lo + (int)(span * (g + 1) / n);   // multigpu.shard_range
+        if (span >= n) {
+            q.sample_begin = s_lo + (int)(span * g / n); q.sample_end = s_lo + (int)(span * (g + 1) / n);   // sample sharding (multigpu.shard_range)
+        } else {
+            q.sample_begin = s_lo; q.sample_end = s_hi;                                                    // fewer samples than GPUs: interleaved
+            q.tile_shard_index = g; q.tile_shard_count = n;                                                // tiles, every sample of each
+        }
         if (q.sample_end > q.sample_begin) {
             rc = render_to_layers(s, &q, s->stream, &plans[(size_t)g], &kis[(size_t)g]);
             if (rc != RT_OK) return rc;

@@ -139,7 +139,7 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS) render_kernel(const R
                     const uint32_t tile = r >> 5, w = r & 31u;
                     const uint32_t ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
                     px = (int)(tx * 8u + (w & 7u)); py = (int)(ty * 4u + (w >> 3));
-                    if (px < a.W && py < a.H) {
+                    if (px < a.W && py < a.H && tile % a.shard_count == a.shard_index) {
                         have_item = true;
                         pix = (uint32_t)py * (uint32_t)a.W + (uint32_t)px;
                         s_cur = a.s_begin + (int)chunk * a.chunk_size;
@@ -316,7 +316,8 @@ __global__ void resolve_u8_kernel(const float4* __restrict__ accum, size_t n_pix
 __global__ void resolve_linear_kernel(const float4* __restrict__ accum, size_t n_pix, float* __restrict__ rgb) {
     for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (size_t)gridDim.x * blockDim.x) {
         const float4 s = accum[p];
-        rgb[3 * p + 0] = s.x / s.w; rgb[3 * p + 1] = s.y / s.w; rgb[3 * p + 2] = s.z / s.w;
+        const bool any = s.w > 0.f;                             // pixels outside this call's tile shard hold no samples: 0
+        rgb[3 * p + 0] = any ? s.x / s.w : 0.f; rgb[3 * p + 1] = any ? s.y / s.w : 0.f; rgb[3 * p + 2] = any ? s.z / s.w : 0.f;
     }
 }
 static int grid_for(size_t n, int block) { size_t g = (n + (size_t)block - 1) / (size_t)block; return (int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1)); }

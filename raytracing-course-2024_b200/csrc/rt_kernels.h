@@ -23,6 +23,7 @@ struct RenderArgs {
     float inv_n_comp;            // 1 / n_comp (MixDistribution::pdf, distributions.rs:194-201)
     int32_t s_begin, s_end, chunk_size, n_chunks;
     uint32_t tiles_x, n_pix_items, total_items;
+    uint32_t shard_index, shard_count;   // interleaved tile sharding: this launch owns tiles t with t % shard_count == shard_index (count >= 1)
     uint32_t stack_entries;
     int32_t node_min;            // v3 phased bursts: box-pair steps run while at least this many lanes want one
     int32_t burst_exit;          // v3: a trace burst ends when this many lanes of the warp have finished their ray (1..32)

@@ -233,7 +233,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                             const uint32_t tile = rr >> 5, w = rr & 31u;
                             const uint32_t ty = tile / a.tiles_x, tx = tile - ty * a.tiles_x;
                             const uint32_t px = tx * 8u + (w & 7u), py = ty * 4u + (w >> 3);
-                            if ((int)px < a.W && (int)py < a.H) {
+                            if ((int)px < a.W && (int)py < a.H && tile % a.shard_count == a.shard_index) {
                                 xy = (py << 16) | px;
                                 s_this = a.s_begin + (int)chunk * a.chunk_size;
                                 pool.sti(F_PIX, s, (int)xy);
