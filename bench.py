@@ -320,7 +320,7 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "scene file scenes/practice7_4.gltf (fixed input, 92 triangles); no synthetic tensors",
             "config": {"workload": f"{args.scene} {W}x{H} {S} spp ray_depth 6, sample-sharded over {world} GPU(s), Philox seed {args.seed}",
-                       "l2_note": "inputs are a 17 KB scene staged in shared memory; each step rewrites the %.0f MB accumulator (> L2 is not needed: nothing is re-read across steps)" % (hbm_bytes / 3 / 1e6),
+                       "l2_note": "inputs are a 21 KB scene staged in shared memory; each step rewrites the %.0f MB accumulator (> L2 is not needed: nothing is re-read across steps)" % (hbm_bytes / 3 / 1e6),
                        "scene_in_shared_memory": bool(info["scene_in_shared_memory"]), "bvh_nodes": info["n_nodes"], "kernel_variant": args.variant},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(info["device_bytes"]) * world, "d2h_bytes_per_step": W * H * 3,
                     "steps": e2e_n, "ms_per_step": e2e_ms / e2e_n},
