@@ -13,7 +13,7 @@ Keys of the JSON line (rank 0):
   value        whole-job Msamples/s, scene resident on the device, device-timed (CUDA events, max over ranks)
   e2e          same metric through the C ABI with HOST buffers: rt_scene_create from host arrays (BVH build +
                H2D scene upload) + render + (reduce) + resolve + D2H of the W*H*3 result, every step
-  roofline     FP32-issue roofline of the render kernel (the scene is ~13 KB and shared-memory
+  roofline     FP32-issue roofline of the render kernel (the scene is ~21 KB and shared-memory
                resident, so HBM is not the bound): achieved = algorithmic flop/sample (fixed constants x counts
                measured by the kernel's own stats mode) x samples / kernel time; peak = FFMA micro-benchmark run
                in this process ("measured here"); hbm_* = the secondary HBM figures
