@@ -398,6 +398,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     }
     plan->variant = kern == 0 ? env_int("RT_KERNEL", 3) : kern;
     if (plan->variant < 1 || plan->variant > 3) return fail(RT_ERR_INVALID, "kernel_variant: unknown kernel");
+    if (plan->variant != 1 && h.ray_depth > 255) return fail(RT_ERR_LIMIT, "ray_depth above 255 (the wavefront kernel packs the remaining depth in 8 bits; kernel_variant 10 has no limit)");
 
     plan->cfg = env_int("RT_WAVE_CFG", 2);
     // sample chunks: enough (pixel, chunk) items to keep every resident lane busy ~4 times over

@@ -246,7 +246,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 }
                 if (state == ST_GEN) {
                     pool.sti(F_S, s, s_this);
-                    call = 0u; attempt = 0; depth = a.ray_depth > 255 ? 255 : a.ray_depth;
+                    call = 0u; attempt = 0; depth = a.ray_depth;                    // <= 255, checked on the host
                     if (STATS) ++c_samples;
                 }
                 // (3) ONE Philox call per live slot: the camera jitter of a new path (call 0) or the next attempt of the
