@@ -398,6 +398,8 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     }
     plan->variant = kern == 0 ? env_int("RT_KERNEL", 3) : kern;
     if (plan->variant < 1 || plan->variant > 3) return fail(RT_ERR_INVALID, "kernel_variant: unknown kernel");
+    if (plan->variant != 1 && (long long)h.ray_depth * std::min(a.max_attempts, 127) + 1 >= (1 << 14))
+        return fail(RT_ERR_LIMIT, "ray_depth x max_attempts exceeds the 14-bit Philox call counter of the wavefront kernel (lower max_attempts, or kernel_variant 10)");
     if (plan->variant != 1 && h.ray_depth > 255) return fail(RT_ERR_LIMIT, "ray_depth above 255 (the wavefront kernel packs the remaining depth in 8 bits; kernel_variant 10 has no limit)");
 
     plan->cfg = env_int("RT_WAVE_CFG", 2);
