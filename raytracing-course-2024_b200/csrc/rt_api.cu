@@ -405,6 +405,15 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     plan->cfg = env_int("RT_WAVE_CFG", 2);
     // sample chunks: enough (pixel, chunk) items to keep every resident lane busy ~4 times over
     int lanes = 0;
+    if (plan->use_smem && placement == 0) {
+        // automatic placement: staging the scene must not cost occupancy (a mid-size blob can push the block past half of the
+        // SM's shared memory: one block per SM instead of two) -- fall back to the global-memory path in that case
+        int with_smem = 0, without = 0;
+        cudaError_t es = rtd::render_resident_lanes(plan->variant, plan->cfg, true, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
+        if (es != cudaSuccess) { cudaGetLastError(); with_smem = 0; }
+        CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, false, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &without));
+        if (with_smem < without) { plan->use_smem = false; a.blob = s->blob_dev; }
+    }
     CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
     const int n_samp = s1 - s0;
     long long want = (4LL * lanes + a.n_pix_items - 1) / a.n_pix_items;

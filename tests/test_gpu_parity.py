@@ -547,3 +547,24 @@ def test_tile_sharding_is_consistent(gpu_rt, kv):
             own[y, x] = ((y // 4) * ((W + 7) // 8) + x // 8) % n == 1
     assert np.array_equal(part[own], full[own]) and not part[~own].any()
     sc.close()
+
+
+def test_automatic_scene_placement_keeps_two_blocks_per_sm(gpu_rt, oracle):
+    """A mid-size scene (184 triangles, ~40 KB blob) would fit the shared-memory staging limit but push the render block past
+    half of the SM's shared memory; the automatic placement must then read the scene through L1/L2 instead (two resident
+    blocks per SM), and both placements must render the same image."""
+    fl = oracle.convert_gltf_to_scene(scene_path("practice7_4"), 96, 54, 64)
+    far = fl.tri_v.copy(); far[:, 0::3] += 50.0                           # a second copy of the room, out of sight
+    kw = dict(width=96, height=54, samples=64, ray_depth=6, bg_color=fl.bg_color, camera_position=fl.camera_position, camera_forward=fl.camera_forward,
+              camera_right=fl.camera_right, camera_up=fl.camera_up, camera_fov_x=fl.camera_fov_x, camera_fov_y=fl.camera_fov_y,
+              tri_v=np.concatenate([fl.tri_v, far]), tri_n=np.concatenate([fl.tri_n, fl.tri_n]),
+              tri_material=np.concatenate([fl.tri_material, fl.tri_material]), tri_emission=np.concatenate([fl.tri_emission, np.zeros_like(fl.tri_emission)]))
+    sc = gpu_rt.Scene.from_arrays(**kw)
+    assert sc.info()["n_tris"] == 184 and sc.info()["scene_in_shared_memory"] == 1           # eligible ...
+    auto, st = sc.render_linear(seed=2)
+    assert st["scene_in_shared_memory"] == 0 and st["blocks_per_sm"] == 2, st                 # ... but not at the price of occupancy
+    forced, st2 = sc.render_linear(seed=2, kernel_variant=2)
+    assert st2["scene_in_shared_memory"] == 1 and st2["blocks_per_sm"] == 1, st2
+    d = np.abs(auto.astype(np.float64) - forced)
+    assert np.median(d) <= 1e-5 * np.abs(auto).mean() and d.mean() <= 2e-2 * np.abs(auto).mean()
+    sc.close()
