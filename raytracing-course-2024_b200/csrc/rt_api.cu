@@ -383,8 +383,8 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     a.shard_count = p->tile_shard_count > 1 ? (uint32_t)p->tile_shard_count : 1u;
     a.shard_index = a.shard_count > 1 ? (uint32_t)p->tile_shard_index : 0u;
     if (p->tile_shard_count > 1 && (p->tile_shard_index < 0 || p->tile_shard_index >= p->tile_shard_count)) return fail(RT_ERR_INVALID, "tile_shard_index must be in [0, tile_shard_count)");
-    a.node_min = std::min(32, std::max(1, env_int("RT_NODE_MIN", 8)));
-    a.burst_exit = std::min(32, std::max(1, env_int("RT_BURST_EXIT", 12)));
+    a.node_min = std::min(32, std::max(1, env_int("RT_NODE_MIN", 10)));
+    a.burst_exit = std::min(32, std::max(1, env_int("RT_BURST_EXIT", 20)));
     a.seed_lo = (uint32_t)(p->seed & 0xffffffffu); a.seed_hi = (uint32_t)(p->seed >> 32);
     plan->stats = p->collect_stats != 0;
     // kernel_variant = 10*kernel + scene placement: kernel 0 auto (= 3), 1 = v1 per-lane megakernel, 2 / 3 = v3 warp-local
