@@ -147,7 +147,8 @@ int rt_resolve_device(const float* accum_dev, int32_t width, int32_t height, uin
  * holds the same scene on device g (rt_scene_load_gltf / rt_scene_create with device = g); GPU g renders samples
  * [g*S/n, (g+1)*S/n) of every pixel, the W*H*4 float accumulators are summed on scenes[0]'s device with one ncclReduce over
  * NVLink (libnccl is loaded with dlopen; RT_NCCL_LIB overrides its name; without NCCL the sum uses peer copies), resolved
- * there (color_to_pixel) and copied to rgb_out.  n = 1 is rt_render.  Same bytes as rt_render up to FP32 summation order. */
+ * there (color_to_pixel) and copied to rgb_out.  n = 1 is rt_render.  Same bytes as rt_render up to FP32 summation order.
+ * With fewer samples than GPUs the frame is sharded by interleaved 8x4-pixel tiles instead (RtRenderParams.tile_shard_*). */
 int rt_render_multi(RtScene* const* scenes, int32_t n_scenes, const RtRenderParams* params, uint8_t* rgb_out, RtStats* stats);
 /* Optional: create the NCCL communicators (seconds) / enable peer access for this device list ahead of the first frame. */
 int rt_multi_init(RtScene* const* scenes, int32_t n_scenes);
@@ -169,7 +170,7 @@ enum {
     RT_FN_PDF_LIGHT = 4,     /* in: point3 l3 (6)                        out: 1         distributions.rs:160-184 */
     RT_FN_PDF_MIX = 5,       /* in: point3 n3 l3 v3 rough (13)           out: 1         distributions.rs:194-201 */
     RT_FN_SAMPLE_COSINE = 6, /* in: n3 u1 u2 (5)                         out: l3 + sphere3 (6)  :54-63           */
-    RT_FN_SAMPLE_VNDF = 7,   /* in: n3 v3 rough u1 u2 (9)                out: l3        :264-274                 */
+    RT_FN_SAMPLE_VNDF = 7,   /* in: n3 v3 rough u1 u2 (9)                out: l3        :264-274 (same distribution, spherical-cap construction) */
     RT_FN_SAMPLE_LIGHT = 8,  /* in: point3 light_index u v (6)           out: l3        :111-125,151-158         */
     RT_FN_PHILOX = 9         /* in: pixel sample call seed_lo (4, as exact integers) out: 4 (u32 as float bits)  */
 };
