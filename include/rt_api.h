@@ -23,7 +23,7 @@
 extern "C" {
 #endif
 
-#define RT_API_VERSION 1
+#define RT_API_VERSION 2
 
 enum {
     RT_OK = 0,
@@ -59,6 +59,24 @@ typedef struct RtSceneDesc {
     const double* tri_emission;       /* n_tris x 3                                (scene.rs:19)          */
 } RtSceneDesc;
 
+/* General primitives: the reference's Object3D { shape, position, rotation } (src/geometry.rs:41-46) with
+ * Shape3D::Box { s } (geometry.rs:27-30) next to Shape3D::Triangle, the dead-but-present Primitive.ior (scene.rs:18), and the
+ * shapes / material of the course's text scene format that reference HEAD no longer has (PLANE, ELLIPSOID, DIELECTRIC: this
+ * repository's own specification).  Planes are the reference's Scene::infinite_primitives (scene.rs:37,
+ * scanned after the BVH, rendering.rs:215-224); every other primitive goes to the BVH (scene.rs:33). */
+enum { RT_SHAPE_TRIANGLE = 0, RT_SHAPE_BOX = 1, RT_SHAPE_ELLIPSOID = 2, RT_SHAPE_PLANE = 3 };
+enum { RT_MATERIAL_PBR = 0,        /* Material { base_color_factor, metallic_factor, metallic_roughness } (scene.rs:6-11)  */
+       RT_MATERIAL_DIELECTRIC = 1  /* own spec: smooth dielectric with Primitive.ior, tinted by base_color on entry         */ };
+typedef struct RtSceneDesc2 {
+    RtSceneDesc base;                 /* n_tris = number of primitives; tri_v row = a,b,c | s,-,- | radii,-,- | normal,-,- ;
+                                         tri_n rows are read for triangles only and are OBJECT-space normals             */
+    const int32_t* shape_kind;        /* n: RT_SHAPE_*                                    (geometry.rs:27-39)             */
+    const double* position;           /* n x 3: Object3D.position                         (geometry.rs:44)                */
+    const double* rotation;           /* n x 4: Object3D.rotation, unit quaternion (i, j, k, w)   (geometry.rs:45)        */
+    const double* ior;                /* n: Primitive.ior                                 (scene.rs:18)                   */
+    const int32_t* material_kind;     /* n: RT_MATERIAL_*                                                                 */
+} RtSceneDesc2;
+
 typedef struct RtSceneInfo {
     int32_t n_tris, n_lights, n_materials;
     int32_t n_nodes;                  /* inner (child-pair) nodes of the device BVH                       */
@@ -70,6 +88,8 @@ typedef struct RtSceneInfo {
     int32_t bvh_builder;              /* 0 = host SAH sweep (default), 1 = GPU LBVH builder (env RT_BVH_BUILDER=gpu) */
     int32_t reserved1;
     double  bvh_build_ms;             /* time spent building the finite-primitive BVH (create_bvh_tree, gltf_to_scene.rs:72) */
+    int32_t n_infinite;               /* planes = Scene::infinite_primitives (scene.rs:37); n_tris counts the finite primitives */
+    int32_t general_primitives;       /* 1: the scene holds boxes / ellipsoids / planes / object transforms / dielectrics    */
 } RtSceneInfo;
 
 typedef struct RtRenderParams {
@@ -115,12 +135,24 @@ int rt_device_count(int32_t* count);
  * and BVH inspection through rt_scene_get_desc / rt_scene_info / rt_scene_get_bvh); every compute entry point
  * fails on it with RT_ERR_CUDA. */
 int rt_scene_load_gltf(const char* path, int32_t width, int32_t height, int32_t samples, int32_t device, RtScene** out);
+/* The course's text scene format (DIMENSIONS, CAMERA_*, RAY_DEPTH, SAMPLES, BG_COLOR, NEW_PRIMITIVE with PLANE / ELLIPSOID / BOX /
+ * TRIANGLE, POSITION, ROTATION, COLOR, EMISSION, METALLIC, DIELECTRIC, IOR).  Reference HEAD has NO parser for it
+ * (main.rs:48 keeps `// let scene = parse_file_content(file_lines);`): grammar recovered from scenes/practice3_*.txt and
+ * scenes/working.txt, semantics = own spec.  width / height / samples > 0 override the file's
+ * DIMENSIONS / SAMPLES (the reference CLI passes them, main.rs:39-41); <= 0 keeps the file's values. */
+int rt_scene_load_text(const char* path, int32_t width, int32_t height, int32_t samples, int32_t device, RtScene** out);
+/* Dispatch on the file extension: ".txt" -> rt_scene_load_text, anything else -> rt_scene_load_gltf (main.rs:45). */
+int rt_scene_load(const char* path, int32_t width, int32_t height, int32_t samples, int32_t device, RtScene** out);
 /* Replaces constructing a `Scene` by hand (scene.rs:22-39): a caller that already has the flat primitives
  * (e.g. the Rust host after its own convert_gltf_to_scene) hands them over; arrays are copied. */
 int rt_scene_create(const RtSceneDesc* desc, int32_t device, RtScene** out);
+/* Same with general primitives (Object3D + Shape3D::Box, geometry.rs:27-46; own-spec shapes and material, see RtSceneDesc2).
+ * Null extension arrays mean: all triangles / zero positions / identity rotations / ior 1 / RT_MATERIAL_PBR. */
+int rt_scene_create2(const RtSceneDesc2* desc, int32_t device, RtScene** out);
 void rt_scene_destroy(RtScene* scene);
 /* Host-side view of the flat scene (pointers stay valid until rt_scene_destroy) -- what the loader produced. */
 int rt_scene_get_desc(const RtScene* scene, RtSceneDesc* out);
+int rt_scene_get_desc2(const RtScene* scene, RtSceneDesc2* out);   /* extension arrays are null for a triangles-only scene */
 int rt_scene_info(const RtScene* scene, RtSceneInfo* out);
 /* Change samples / image size without re-uploading geometry (main.rs:39-41 are per-run arguments). */
 int rt_scene_set_frame(RtScene* scene, int32_t width, int32_t height, int32_t samples);
@@ -158,6 +190,10 @@ int rt_multi_init(RtScene* const* scenes, int32_t n_scenes);
  * precision 32 = the production FP32 traversal the renderer uses; 64 = same traversal with f64 triangle tests.
  * tri_id = ORIGINAL (load-order) triangle index or -1; t = hit distance (inf on miss). */
 int rt_trace_primary(RtScene* scene, const double* rays, int64_t n, int32_t precision, int32_t* tri_id, double* t);
+/* Same query returning what get_ray_color reads from the hit (rendering.rs:96-101,107): out = n x 9 doubles: t,
+ * normal_geometry xyz (world, facing the ray), normal_shading xyz (normalised; object space -- the reference does not rotate
+ * it back, geometry.rs:245-249), original primitive index (-1 on a miss), is_outer_to_inner.  FP32 traversal. */
+int rt_trace_hits(RtScene* scene, const double* rays, int64_t n, double* out);
 /* Camera rays of get_ray_to_pixel (rendering.rs:71-84) for explicit jitter: xy n x 2 ints, xi n x 2 doubles ->
  * rays n x 6 doubles, computed on the device in FP32 exactly as the render kernel does. */
 int rt_primary_rays(RtScene* scene, const int32_t* xy, const double* xi, int64_t n, double* rays_out);
@@ -172,7 +208,9 @@ enum {
     RT_FN_SAMPLE_COSINE = 6, /* in: n3 u1 u2 (5)                         out: l3 + sphere3 (6)  :54-63           */
     RT_FN_SAMPLE_VNDF = 7,   /* in: n3 v3 rough u1 u2 (9)                out: l3        :264-274 (same distribution, spherical-cap construction) */
     RT_FN_SAMPLE_LIGHT = 8,  /* in: point3 light_index u v (6)           out: l3        :111-125,151-158         */
-    RT_FN_PHILOX = 9         /* in: pixel sample call seed_lo (4, as exact integers) out: 4 (u32 as float bits)  */
+    RT_FN_PHILOX = 9,        /* in: pixel sample call seed_lo (4, as exact integers) out: 4 (u32 as float bits)  */
+    RT_FN_SAMPLE_LIGHT_GEN = 10, /* in: point3 light_index u1 u2 x01 sign (8)    out: l3   :84-125 incl. the Box arm :86-110 (general scenes) */
+    RT_FN_DIELECTRIC = 11    /* in: n3 v3 ior outer u (9)                out: l3 + refracted flag (4)   own spec         */
 };
 int rt_eval(RtScene* scene_or_null, int32_t fn, const float* in, int64_t n, float* out);
 

@@ -12,6 +12,10 @@ import subprocess
 import numpy as np
 
 from .gltf_ref import FlatScene, convert_gltf_to_scene  # noqa: F401
+from .text_ref import parse_text_scene  # noqa: F401
+
+SHAPE_TRIANGLE, SHAPE_BOX, SHAPE_ELLIPSOID, SHAPE_PLANE = range(4)
+MAT_PBR, MAT_DIELECTRIC = 0, 1
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _LIB_PATH = os.path.join(_HERE, "_build", "liboracle.so")
@@ -28,6 +32,8 @@ class OrSceneDesc(C.Structure):
         ("camera_fov_x", C.c_double), ("camera_fov_y", C.c_double),
         ("n_tris", C.c_int32), ("_pad", C.c_int32),
         ("tri_v", _dp), ("tri_n", _dp), ("tri_material", _dp), ("tri_emission", _dp),
+        ("kind", C.POINTER(C.c_int32)), ("position", _dp), ("rotation", _dp), ("ior", _dp), ("mat_kind", C.POINTER(C.c_int32)),
+        ("max_attempts", C.c_int32), ("_pad2", C.c_int32),
     ]
 
 
@@ -37,7 +43,7 @@ class OrInfo(C.Structure):
 
 class OrStats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("node_tests", "tri_tests", "segments", "vertices", "attempts", "light_node_tests",
-                                          "light_tri_tests", "vndf_assert_fail", "nan_pixels", "samples")] + [("seconds", C.c_double)]
+                                          "light_tri_tests", "vndf_assert_fail", "nan_pixels", "samples")] + [("seconds", C.c_double), ("attempt_cap_hits", C.c_uint64)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -76,7 +82,8 @@ def _p(a, t=C.c_double):
 class OracleScene:
     """Scene (scene.rs:22-39) built from a FlatScene: both BVHs are built by the restated bvh.rs builder."""
 
-    def __init__(self, flat: FlatScene):
+    def __init__(self, flat: FlatScene, max_attempts: int = 0):
+        """max_attempts = 0: the reference's unbounded rejection loop; > 0: the path ends after that many failed attempts."""
         self.flat = flat
         L = lib()
         d = OrSceneDesc()
@@ -87,6 +94,15 @@ class OracleScene:
         d.n_tris = flat.n_tris
         self._keep = [_d(flat.tri_v), _d(flat.tri_n), _d(flat.tri_material), _d(flat.tri_emission)]
         d.tri_v, d.tri_n, d.tri_material, d.tri_emission = (_p(a) for a in self._keep)
+        if flat.kind is not None:
+            n = flat.n_tris
+            ex = [np.ascontiguousarray(flat.kind, dtype=np.int32), _d(flat.position if flat.position is not None else np.zeros((n, 3))),
+                  _d(flat.rotation if flat.rotation is not None else np.tile([0.0, 0.0, 0.0, 1.0], (n, 1))),
+                  _d(flat.ior if flat.ior is not None else np.ones(n)),
+                  np.ascontiguousarray(flat.mat_kind if flat.mat_kind is not None else np.zeros(n), dtype=np.int32)]
+            self._keep += ex
+            d.kind, d.position, d.rotation, d.ior, d.mat_kind = _p(ex[0], C.c_int32), _p(ex[1]), _p(ex[2]), _p(ex[3]), _p(ex[4], C.c_int32)
+        d.max_attempts = int(max_attempts)
         self._h = C.c_void_p(L.or_scene_create(C.byref(d)))
         self.width, self.height, self.samples = flat.width, flat.height, flat.samples
 
@@ -149,8 +165,9 @@ class OracleScene:
         return {"tri_id": tid, "t": t, "u": u, "v": v, "second_t": second, "stats": st.as_dict()}
 
     def trace_hits(self, rays) -> np.ndarray:
+        """(n, 9): t, normal_geometry xyz, normal_shading xyz, original primitive id, is_outer_to_inner."""
         rays = _d(rays)
-        out = np.zeros((rays.shape[0], 8), dtype=np.float64)
+        out = np.zeros((rays.shape[0], 9), dtype=np.float64)
         lib().or_trace_hits(self._h, _p(rays), C.c_int64(rays.shape[0]), _p(out))
         return out
 
@@ -166,11 +183,14 @@ class OracleScene:
         lib().or_pdf_mix(self._h, _p(point), _p(n), _p(l), _p(v), _p(mat), C.c_int64(point.shape[0]), _p(out))
         return out
 
-    def sample_light(self, light_idx, point, uv):
+    def sample_light(self, light_idx, point, draws):
+        """draws (n, 2..4): triangle (u, v); box (x01, sign, c1, c2 in [-1, 1)); ellipsoid (unit sphere xyz) -- see or_sample_light."""
         light_idx = np.ascontiguousarray(light_idx, dtype=np.int32)
-        point, uv = _d(point), _d(uv)
+        point, draws = _d(point), _d(draws)
+        if draws.shape[1] < 4:
+            draws = _d(np.concatenate([draws, np.zeros((draws.shape[0], 4 - draws.shape[1]))], axis=1))
         out = np.zeros((point.shape[0], 3))
-        lib().or_sample_light(self._h, _p(light_idx, C.c_int32), _p(point), _p(uv), C.c_int64(point.shape[0]), _p(out))
+        lib().or_sample_light(self._h, _p(light_idx, C.c_int32), _p(point), _p(draws), C.c_int64(point.shape[0]), _p(out))
         return out
 
 
@@ -245,6 +265,30 @@ def aabb_first_hit(o, d, mn, mx):
     outer = C.c_int32(0)
     hit = lib().or_aabb_first_hit(_p(o), _p(d), _p(mn), _p(mx), C.byref(t), C.byref(outer))
     return (bool(hit), t.value, bool(outer.value))
+
+
+def intersect_shape(kind, params, o, d, upper=np.inf):
+    """Object-space hits of one shape (geometry.rs:79-91 + own-spec arms): list of (t, normal xyz, is_outer_to_inner)."""
+    params = _d(np.resize(np.asarray(params, dtype=np.float64), 9) if np.size(params) < 9 else params)
+    o, d = _d(o), _d(d)
+    out = np.zeros(10)
+    lib().or_intersect_shape.restype = C.c_int
+    n = lib().or_intersect_shape(C.c_int32(kind), _p(params), _p(o), _p(d), C.c_double(upper), _p(out))
+    return [(out[5 * k], out[5 * k + 1:5 * k + 4].copy(), bool(out[5 * k + 4])) for k in range(n)]
+
+
+def quat_transform(q_ijkw, v, conjugate=False):
+    q, v = _d(q_ijkw), _d(v)
+    out = np.zeros(3)
+    lib().or_quat_transform(_p(q), _p(v), C.c_int32(1 if conjugate else 0), _p(out))
+    return out
+
+
+def object_aabb(kind, params, position, q_ijkw):
+    params = _d(np.resize(np.asarray(params, dtype=np.float64), 9) if np.size(params) < 9 else params)
+    out = np.zeros(6)
+    lib().or_object_aabb(C.c_int32(kind), _p(params), _p(_d(position)), _p(_d(q_ijkw)), _p(out))
+    return out[:3], out[3:]
 
 
 def rng_u64(seed: int, cnt: int) -> np.ndarray:

@@ -54,6 +54,13 @@ class FlatScene:
     tri_n: np.ndarray = field(default_factory=lambda: np.zeros((0, 9)))       # a_norm, b_norm, c_norm
     tri_material: np.ndarray = field(default_factory=lambda: np.zeros((0, 5)))  # base rgb, metallic, roughness
     tri_emission: np.ndarray = field(default_factory=lambda: np.zeros((0, 3)))
+    # general primitives (text scenes, oracle/text_ref.py); None = triangles with identity transforms (all the glTF loader emits).
+    # For kind != 0 the first three entries of a tri_v row are the box half sizes / ellipsoid radii / plane normal.
+    kind: np.ndarray | None = None         # (n,) int32: 0 triangle, 1 box, 2 ellipsoid, 3 plane   (geometry.rs:27-39 + own spec)
+    position: np.ndarray | None = None     # (n, 3)  Object3D.position (geometry.rs:44)
+    rotation: np.ndarray | None = None     # (n, 4)  Object3D.rotation as (i, j, k, w)  (geometry.rs:45)
+    ior: np.ndarray | None = None          # (n,)    Primitive.ior (scene.rs:18)
+    mat_kind: np.ndarray | None = None     # (n,) int32: 0 metallic-roughness (scene.rs:6-11), 1 dielectric (own spec)
 
     @property
     def n_tris(self) -> int:
@@ -61,8 +68,11 @@ class FlatScene:
 
     @property
     def light_ids(self) -> np.ndarray:
-        # gltf_to_scene.rs:240  `if emission.norm() > EPS`
-        return np.nonzero(np.linalg.norm(self.tri_emission, axis=1) > EPS)[0].astype(np.int32)
+        # gltf_to_scene.rs:240  `if emission.norm() > EPS`; planes (infinite_primitives) are never lights
+        lit = np.linalg.norm(self.tri_emission, axis=1) > EPS
+        if self.kind is not None:
+            lit &= np.asarray(self.kind) != 3
+        return np.nonzero(lit)[0].astype(np.int32)
 
 
 def _quat_mul(a, b):

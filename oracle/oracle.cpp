@@ -12,9 +12,18 @@
 //  and its Rust toolchain is absent here, so this restatement is pinned only by the
 // hand-derived known answers of SURVEY.md A.3 (tests/test_oracle_kat.py) and by its own invariants.
 //
+// Two kinds of content, marked at every function:
+//   [REF]       follows the cited reference lines (triangles, boxes, Object3D transforms, AABBs, BVH, samplers, BRDF);
+//   [OWN SPEC]  has NO counterpart at reference HEAD: the text-scene shapes PLANE and ELLIPSOID, the DIELECTRIC
+//               material and ellipsoid light sampling.  The reference's parser and those shapes were deleted before
+//               HEAD (main.rs:48 keeps `// let scene = parse_file_content(file_lines);`, scene.rs:18,37 and
+//               geometry.rs:23 keep the dead fields `ior`, `infinite_primitives`, `is_outer_to_inner`).  Their
+//               semantics are declared in DESIGN.md section 12 and restated here so that the device has a checker.
+//
 // Third-party arithmetic restated from its published definition (crate versions are caret ranges, no lockfile):
 //   nalgebra 0.32 : Vector3 dot/cross/normalize (v / |v|), Matrix3::try_inverse (cofactors / det, None iff
-//                   det == 0), UnitQuaternion identity transform (exact no-op).
+//                   det == 0), UnitQuaternion * Vector3 (t = 2 q.v x p;  p' = t w + q.v x t + p; the identity
+//                   quaternion is an exact no-op), conjugate (negated vector part).
 //   rand 0.8 / rand_xoshiro 0.6 : xoshiro256** seeded through SplitMix64, gen::<f64>() = (u64 >> 11) * 2^-53,
 //                   gen_range(0.0..1.0) = [1,2)-mantissa trick, gen_range(0..n) = widening-multiply rejection.
 //   rand_distr 0.4 Normal : the ziggurat tables are not available here; a Marsaglia polar normal is used
@@ -79,17 +88,28 @@ struct Aabb {                                                                   
         return true;
     }
 };
-// scene.rs:13-20 with Object3D{Shape3D::Triangle, position 0, rotation identity} flattened (the only shape the
-// glTF loader emits, gltf_to_scene.rs:202-214).  orig_id = index in load order (used for hit-id parity).
-struct Primitive { V3 a, b, c, a_norm, b_norm, c_norm; Aabb aabb; Material material; V3 emission; int orig_id; };
+// geometry.rs:27-46 Shape3D + Object3D and scene.rs:13-20 Primitive, flattened into one struct.  [REF] kinds: TRIANGLE, BOX
+// (half sizes s).  [OWN SPEC] kinds: ELLIPSOID (radii in s), PLANE (unit normal in s; lives in Scene::infinite_primitives).
+// rotation = nalgebra UnitQuaternion (i, j, k, w).  mat_kind 0 = the metallic-roughness Material of scene.rs:6-11,
+// 1 = [OWN SPEC] dielectric (uses the reference's dead field `ior`, scene.rs:18).  orig_id = index in load order.
+enum { SHAPE_TRIANGLE = 0, SHAPE_BOX = 1, SHAPE_ELLIPSOID = 2, SHAPE_PLANE = 3 };
+enum { MAT_PBR = 0, MAT_DIELECTRIC = 1 };
+struct Quat { Fp i, j, k, w; };
+struct Primitive {
+    int kind;
+    V3 a, b, c, a_norm, b_norm, c_norm;   // Shape3D::Triangle
+    V3 s;                                 // Shape3D::Box { s } | ellipsoid radii | plane normal
+    V3 position; Quat rotation; bool identity;   // Object3D (identity: rotation == 1 and position == 0 -> the transforms are exact no-ops)
+    Aabb aabb; Material material; Fp ior; int mat_kind; V3 emission; int orig_id;
+};
 
 struct Counters {
     uint64_t node_tests, tri_tests, segments, vertices, attempts, light_node_tests, light_tri_tests;
-    uint64_t vndf_assert_fail, nan_pixels, samples;
+    uint64_t vndf_assert_fail, nan_pixels, samples, attempt_cap_hits;
 };
 
 // ------------------------------------------------------------------------------------------------ geometry
-// geometry.rs:93-138  intersect_with_triangle: solve [b-a, c-a, -d] (u,v,t)^T = o - a with Matrix3::try_inverse.
+// [REF] geometry.rs:93-138  intersect_with_triangle: solve [b-a, c-a, -d] (u,v,t)^T = o - a with Matrix3::try_inverse.
 static bool intersect_with_triangle(const Ray& ray, Fp upper_bound, const Primitive& p, Intersection* out,
                                     Fp* uo = nullptr, Fp* vo = nullptr) {
     V3 c0 = p.b - p.a, c1 = p.c - p.a, c2 = -ray.direction;
@@ -124,6 +144,118 @@ static bool intersect_with_triangle(const Ray& ray, Fp upper_bound, const Primit
 }
 
 static inline void sort2(Fp x, Fp y, Fp* lo, Fp* hi) { if (x < y) { *lo = x; *hi = y; } else { *lo = y; *hi = x; } }   // geometry.rs:71-77
+static inline Fp signum(Fp x) { return x != x ? x : (std::signbit(x) ? -1.0 : 1.0); }   // f64::signum: +-1 also for +-0, NaN for NaN
+
+// [REF] geometry.rs:140-194 intersect_with_box: slab test in object space with `d + 0.001*EPS` denominators; up to two
+// hits, entry (outer -> inner) first, each kept iff 0 < t < upper_bound; face normal chosen by `s - |p| < EPS` with the
+// x, y, z priority of :161-169 (z is the fall-through).  Returns the number of hits written to out[0..2).
+static int intersect_with_box(const Ray& ray, Fp upper_bound, V3 s, Intersection* out) {
+    Fp tx0, tx1, ty0, ty1, tz0, tz1;
+    sort2((-s.x - ray.origin.x) / (ray.direction.x + 0.001 * EPS), (s.x - ray.origin.x) / (ray.direction.x + 0.001 * EPS), &tx0, &tx1);
+    sort2((-s.y - ray.origin.y) / (ray.direction.y + 0.001 * EPS), (s.y - ray.origin.y) / (ray.direction.y + 0.001 * EPS), &ty0, &ty1);
+    sort2((-s.z - ray.origin.z) / (ray.direction.z + 0.001 * EPS), (s.z - ray.origin.z) / (ray.direction.z + 0.001 * EPS), &tz0, &tz1);
+    Fp t_min = std::max(tx0, std::max(ty0, tz0));
+    Fp t_max = std::min(tx1, std::min(ty1, tz1));
+    int n = 0;
+    if (t_min <= t_max) {
+        auto calculate_norm = [s](V3 p) {
+            if (s.x - std::fabs(p.x) < EPS) return v3(signum(p.x), 0.0, 0.0);
+            if (s.y - std::fabs(p.y) < EPS) return v3(0.0, signum(p.y), 0.0);
+            return v3(0.0, 0.0, signum(p.z));
+        };
+        if (t_min > 0.0 && t_min < upper_bound) {
+            V3 nm = calculate_norm(ray.origin + ray.direction * t_min);
+            out[n].offset = t_min; out[n].normal_geometry = nm; out[n].normal_shading = nm; out[n].is_outer_to_inner = true; ++n;
+        }
+        if (t_max > 0.0 && t_max < upper_bound) {
+            V3 nm = calculate_norm(ray.origin + ray.direction * t_max);
+            out[n].offset = t_max; out[n].normal_geometry = -nm; out[n].normal_shading = -nm; out[n].is_outer_to_inner = false; ++n;
+        }
+    }
+    return n;
+}
+
+// [OWN SPEC] (no ellipsoid exists at reference HEAD) -- shaped like intersect_with_box: object
+// space, up to two hits, entry first, each kept iff 0 < t < upper_bound.  |(o + t d) / r|^2 = 1 solved with the half-b
+// form; outward normal = normalize(p / r^2), negated (is_outer_to_inner = false) on the exit hit.
+static int intersect_with_ellipsoid(const Ray& ray, Fp upper_bound, V3 r, Intersection* out) {
+    V3 od = cdiv(ray.origin, r), dd = cdiv(ray.direction, r);
+    Fp a = dot(dd, dd), hb = dot(od, dd), c = dot(od, od) - 1.0;
+    Fp disc = hb * hb - a * c;
+    int n = 0;
+    if (!(disc >= 0.0)) return 0;
+    Fp sq = std::sqrt(disc);
+    Fp t1 = (-hb - sq) / a, t2 = (-hb + sq) / a;
+    auto outward = [r](V3 p) { return normalize(cdiv(cdiv(p, r), r)); };
+    if (t1 > 0.0 && t1 < upper_bound) {
+        V3 nm = outward(ray.origin + ray.direction * t1);
+        out[n].offset = t1; out[n].normal_geometry = nm; out[n].normal_shading = nm; out[n].is_outer_to_inner = true; ++n;
+    }
+    if (t2 > 0.0 && t2 < upper_bound) {
+        V3 nm = outward(ray.origin + ray.direction * t2);
+        out[n].offset = t2; out[n].normal_geometry = -nm; out[n].normal_shading = -nm; out[n].is_outer_to_inner = false; ++n;
+    }
+    return n;
+}
+
+// [OWN SPEC] (no plane exists at reference HEAD): the plane through the object origin with unit normal nrm, object space.
+// t = -(o.n)/(d.n), kept iff 0 < t < upper_bound; the normal faces the ray, is_outer_to_inner = the ray arrives from the
+// side the normal points to.  d.n == 0 gives +-inf / NaN, which the comparisons reject.
+static int intersect_with_plane(const Ray& ray, Fp upper_bound, V3 nrm, Intersection* out) {
+    Fp dn = dot(ray.direction, nrm);
+    Fp t = -dot(ray.origin, nrm) / dn;
+    if (t > 0.0 && t < upper_bound) {
+        bool front = dn < 0.0;
+        out[0].offset = t; out[0].normal_geometry = front ? nrm : -nrm; out[0].normal_shading = out[0].normal_geometry; out[0].is_outer_to_inner = front;
+        return 1;
+    }
+    return 0;
+}
+
+// [REF] geometry.rs:79-91 intersect_all_points: dispatch on the shape ([OWN SPEC] arms for ellipsoid / plane).
+static int intersect_all_points(const Ray& ray, const Primitive& p, Fp upper_bound, Intersection* out, Fp* uo = nullptr, Fp* vo = nullptr) {
+    switch (p.kind) {
+        case SHAPE_BOX: return intersect_with_box(ray, upper_bound, p.s, out);
+        case SHAPE_ELLIPSOID: return intersect_with_ellipsoid(ray, upper_bound, p.s, out);
+        case SHAPE_PLANE: return intersect_with_plane(ray, upper_bound, p.s, out);
+        default: return intersect_with_triangle(ray, upper_bound, p, out, uo, vo) ? 1 : 0;
+    }
+}
+
+// nalgebra 0.32 `UnitQuaternion * Vector3` (= transform_vector):  t = 2 (q.v x p);  p' = t * q.w + q.v x t + p.
+static inline V3 quat_transform(const Quat& q, V3 p) {
+    V3 qv = v3(q.i, q.j, q.k);
+    V3 t = cross(qv, p) * 2.0;
+    V3 c = cross(qv, t);
+    return t * q.w + c + p;
+}
+static inline Quat quat_conjugate(const Quat& q) { Quat r = {-q.i, -q.j, -q.k, q.w}; return r; }
+
+// [REF] geometry.rs:226-251 intersect_ray_with_object3d_all_points: ray into object space (origin - position, both
+// rotated by the CONJUGATE quaternion), all hits with upper bound +inf, normal_geometry rotated back -- normal_shading
+// is NOT rotated back (:245-249 touch normal_geometry only).  Identity objects skip the rotations (exact no-ops).
+static int intersect_ray_with_object3d_all_points(const Ray& ray, const Primitive& p, Intersection* out, Ray* rotated_ray, Fp upper_bound = FP_INF,
+                                                  Fp* uo = nullptr, Fp* vo = nullptr) {
+    Ray rr;
+    if (p.identity) rr = ray;
+    else {
+        Quat qc = quat_conjugate(p.rotation);
+        rr.origin = quat_transform(qc, ray.origin - p.position);
+        rr.direction = quat_transform(qc, ray.direction);
+    }
+    int n = intersect_all_points(rr, p, upper_bound, out, uo, vo);
+    if (!p.identity) for (int k = 0; k < n; ++k) out[k].normal_geometry = quat_transform(p.rotation, out[k].normal_geometry);
+    if (rotated_ray) *rotated_ray = rr;
+    return n;
+}
+// [REF] geometry.rs:196-223 intersect_ray_with_object3d: same transform, FIRST hit below min_dist (geometry.rs:51-58).
+static bool intersect_ray_with_object3d(const Ray& ray, const Primitive& p, Fp min_dist, Intersection* out) {
+    Intersection hits[2];
+    int n = intersect_ray_with_object3d_all_points(ray, p, hits, nullptr, min_dist);
+    if (n == 0) return false;
+    *out = hits[0];
+    return true;
+}
 
 // geometry.rs:140-194 intersect_with_box reduced to what bvh.rs:146-166 consumes: the FIRST hit of the list
 // (entry if 0 < t_min < upper, else exit if 0 < t_max < upper) with its is_outer_to_inner flag.  Normals of the
@@ -155,13 +287,28 @@ static bool get_aabb_intersection(const Ray& ray, const Aabb& aabb, Fp* t_out, b
 static inline V3 reflect_vec(V3 v, V3 n) { Fp projection = dot(v, n); return -v + (2.0 * projection) * n; }   // geometry.rs:65-69
 
 // ------------------------------------------------------------------------------------------------ aabb.rs
-// aabb.rs:53-94 for a triangle with identity rotation and zero position: the 8 corners of the EPS-padded
-// shape box pass through an exact identity transform, so min/max are the padded bounds themselves.
-static Aabb calculate_aabb_for_object(const Primitive& p) {
+// [REF] aabb.rs:53-65 calculate_aabb_for_shape: EPS-padded local bounds ([OWN SPEC] arm: ellipsoid = +-radii; planes are
+// never boxed, they live in infinite_primitives).
+static Aabb calculate_aabb_for_shape(const Primitive& p) {
     V3 eps = v3(EPS, EPS, EPS);
     Aabb r;
-    r.min = vinf(vinf(p.a, p.b), p.c) - eps;
-    r.max = vsup(vsup(p.a, p.b), p.c) + eps;
+    if (p.kind == SHAPE_TRIANGLE) { r.min = vinf(vinf(p.a, p.b), p.c) - eps; r.max = vsup(vsup(p.a, p.b), p.c) + eps; }
+    else { r.min = -p.s - eps; r.max = p.s + eps; }
+    return r;
+}
+// [REF] aabb.rs:75-94 calculate_aabb_for_object: bounds of the 8 rotated + translated corners of the shape box.  For an
+// identity object the transform is an exact no-op, so min/max are the padded shape bounds themselves.
+static Aabb calculate_aabb_for_object(const Primitive& p) {
+    Aabb sh = calculate_aabb_for_shape(p);
+    if (p.identity) return sh;
+    Aabb r = Aabb::empty();
+    for (int xm = 0; xm < 2; ++xm)
+        for (int ym = 0; ym < 2; ++ym)
+            for (int zm = 0; zm < 2; ++zm) {
+                V3 point = v3(xm ? sh.max.x : sh.min.x, ym ? sh.max.y : sh.min.y, zm ? sh.max.z : sh.min.z);   // order irrelevant: min/max are commutative
+                V3 op = quat_transform(p.rotation, point) + p.position;
+                r.min = vinf(r.min, op); r.max = vsup(r.max, op);
+            }
     return r;
 }
 static Aabb calculate_aabb(const Primitive* s, size_t n) {      // aabb.rs:96-106
@@ -250,10 +397,11 @@ static int validate_bvh(const BvhTree& t) {
     return bad;
 }
 
-struct BvhIntersection { Intersection hit; const Primitive* primitive; Fp u, v; };   // bvh.rs:168-172 (one hit per triangle)
+// bvh.rs:168-172: all hits of one primitive (ArrayVec<_, 2>), the object-space ray and the primitive.  hit == hits[0].
+struct BvhIntersection { Intersection hit; Intersection hits[2]; int n_hits; Ray rotated_ray; const Primitive* primitive; Fp u, v; };
 
 // bvh.rs:249-297 nearest: unordered DFS (left, then right), prune iff best < t_box_first && entering, leaf
-// prims tested with upper = +inf and filtered by strict `<` afterwards (geometry.rs:244, bvh.rs:268-269).
+// prims tested with upper = +inf; a primitive competes with its FIRST hit only (points.0[0], bvh.rs:269) under strict `<`.
 static void nearest_impl(const Ray& ray, const BvhTree& t, size_t idx, BvhIntersection* res, bool* found, Fp* shortest, Counters* c) {
     const BvhNode& node = t.nodes[idx];
     Fp tb; bool outer;
@@ -262,10 +410,12 @@ static void nearest_impl(const Ray& ray, const BvhTree& t, size_t idx, BvhInters
     if (*shortest < tb && outer) return;
     if (node.left_child_index == NO_CHILD) {
         for (size_t i = node.content_start; i < node.content_start + node.content_length; ++i) {
-            Intersection h; Fp u, v;
+            Intersection h[2]; Fp u = 1.0 / 3.0, v = 1.0 / 3.0; Ray rr;
             ++c->tri_tests;
-            if (intersect_with_triangle(ray, FP_INF, t.primitives[i], &h, &u, &v) && h.offset < *shortest) {
-                *shortest = h.offset; res->hit = h; res->primitive = &t.primitives[i]; res->u = u; res->v = v; *found = true;
+            int n = intersect_ray_with_object3d_all_points(ray, t.primitives[i], h, &rr, FP_INF, &u, &v);
+            if (n > 0 && h[0].offset < *shortest) {
+                *shortest = h[0].offset; res->hit = h[0]; res->hits[0] = h[0]; res->hits[1] = h[1]; res->n_hits = n; res->rotated_ray = rr;
+                res->primitive = &t.primitives[i]; res->u = u; res->v = v; *found = true;
             }
         }
     } else {
@@ -275,11 +425,13 @@ static void nearest_impl(const Ray& ray, const BvhTree& t, size_t idx, BvhInters
 }
 static bool intersect_with_bvh_nearest_point(const Ray& ray, const BvhTree& t, BvhIntersection* res, Counters* c) {   // :231-247
     bool found = false; Fp nearest = FP_INF;
+    if (t.nodes.empty()) return false;
     nearest_impl(ray, t, t.nodes.size() - 1, res, &found, &nearest, c);
     return found;
 }
 
-// bvh.rs:190-229 all points (no pruning), used on the light BVH by the pdf.
+// bvh.rs:190-229 all points (no pruning), used on the light BVH by the pdf: every primitive with at least one hit
+// contributes ALL its hits (both faces of a box).
 static void all_points_impl(const Ray& ray, const BvhTree& t, size_t idx, std::vector<BvhIntersection>* out, Counters* c) {
     const BvhNode& node = t.nodes[idx];
     Fp tb; bool outer;
@@ -287,9 +439,10 @@ static void all_points_impl(const Ray& ray, const BvhTree& t, size_t idx, std::v
     if (!get_aabb_intersection(ray, node.aabb, &tb, &outer)) return;       // intersects() :146-155
     if (node.left_child_index == NO_CHILD) {
         for (size_t i = node.content_start; i < node.content_start + node.content_length; ++i) {
-            BvhIntersection bi;
+            BvhIntersection bi; bi.u = bi.v = 1.0 / 3.0;
             ++c->light_tri_tests;
-            if (intersect_with_triangle(ray, FP_INF, t.primitives[i], &bi.hit, &bi.u, &bi.v)) { bi.primitive = &t.primitives[i]; out->push_back(bi); }
+            bi.n_hits = intersect_ray_with_object3d_all_points(ray, t.primitives[i], bi.hits, &bi.rotated_ray, FP_INF, &bi.u, &bi.v);
+            if (bi.n_hits > 0) { bi.hit = bi.hits[0]; bi.primitive = &t.primitives[i]; out->push_back(bi); }
         }
     } else {
         all_points_impl(ray, t, node.left_child_index, out, c);
@@ -318,6 +471,11 @@ struct Rng {
             if ((uint64_t)m <= zone) return (size_t)(m >> 64);
         }
     }
+    Fp gen_range(Fp low, Fp high) {                                          // gen_range(low..high), rand 0.8 UniformFloat::sample_single
+        Fp scale = high - low;
+        for (;;) { Fp res = gen_range01() * scale + low; if (res < high) return res; }
+    }
+    bool gen_bool_half() { return next_u64() < (1ull << 63); }                // gen_bool(0.5): Bernoulli p_int = 2^63, sample = (u64 < p_int)
     Fp normal() {                                                            // Normal::new(0,1).sample(rng) -- polar method, see header
         if (has_spare) { has_spare = false; return spare; }
         for (;;) {
@@ -333,7 +491,9 @@ struct Scene {                                                                //
     V3 bg_color, camera_position, camera_forward, camera_right, camera_up;
     Fp camera_fov_x, camera_fov_y;
     BvhTree bvh_finite_primitives, bvh_light_sources;
+    std::vector<Primitive> infinite_primitives;                               // scene.rs:37 (planes; empty for glTF input)
     bool has_lights;
+    int max_attempts;                                                         // NOT in the reference: 0 = unbounded rejection loop (rendering.rs:102-110)
 };
 
 // ------------------------------------------------------------------------------------------------ distributions.rs
@@ -342,22 +502,73 @@ static V3 cosine_sample_from_sphere(V3 n, V3 uniform_unit) { return normalize(un
 static V3 cosine_sample(V3 n, Rng* rng) { Fp a = rng->normal(), b = rng->normal(), c = rng->normal(); return cosine_sample_from_sphere(n, normalize(v3(a, b, c))); }
 static Fp cosine_pdf(V3 n, V3 l) { return std::max(0.0, dot(normalize(l), n)) / FP_PI; }                     // :65-67
 
-static Fp get_local_pdf(const Primitive& p) { Fp area = norm(cross(p.b - p.a, p.c - p.a)) * 0.5; return 1.0 / area; }   // :70-81 (triangle arm)
+// [REF] :70-81 get_local_pdf: 1 / surface area (box: 8 (sx sy + sy sz + sz sx); triangle: |e1 x e2| / 2).
+// [OWN SPEC] ellipsoid arm: the sampler maps a uniform unit-sphere point u to r (.) u, whose area density at the
+// object-space point p = r (.) u is 1 / (4 pi sqrt((u.x ry rz)^2 + (rx u.y rz)^2 + (rx ry u.z)^2)).
+static Fp get_local_pdf(const Primitive& p, V3 local_point) {
+    if (p.kind == SHAPE_BOX) { Fp area = (p.s.x * p.s.y + p.s.y * p.s.z + p.s.z * p.s.x) * 8.0; return 1.0 / area; }
+    if (p.kind == SHAPE_ELLIPSOID) {
+        V3 u = cdiv(local_point, p.s), r = p.s;
+        Fp j = std::sqrt(powi2(u.x * r.y * r.z) + powi2(r.x * u.y * r.z) + powi2(r.x * r.y * u.z));
+        return 1.0 / (4.0 * FP_PI * j);
+    }
+    Fp area = norm(cross(p.b - p.a, p.c - p.a)) * 0.5;
+    return 1.0 / area;
+}
 
-// :111-125 DirectLightSamplingDistribution::sample_unit_vector, triangle arm, with the two uniforms explicit.
+// [REF] :121-124: object space -> world (rotation.transform_vector(local) + position), direction = normalize(global - point).
+static V3 light_direction_from_local(const Primitive& p, V3 point, V3 local) {
+    V3 global = p.identity ? local : quat_transform(p.rotation, local) + p.position;
+    return normalize(global - point);
+}
+// [REF] :111-125 DirectLightSamplingDistribution::sample_unit_vector, triangle arm, with the two uniforms explicit.
 static V3 light_sample_from_uv(const Primitive& p, V3 point, Fp u, Fp v) {
     if (!(u + v < 1.0)) { u = 1.0 - u; v = 1.0 - v; }
     V3 local = p.a + (p.b - p.a) * u + (p.c - p.a) * v;
-    return normalize(local - point);          // rotation identity, position 0 (:121-124)
+    return light_direction_from_local(p, point, local);
+}
+// [REF] :86-110 box arm with the draws explicit: x in [0, wx+wy+wz) picks the face pair by area, sign picks the face,
+// (c1, c2) are the two in-face coordinates in draw order (gen_range(-s.y..s.y) then (-s.z..s.z) for an x face, ...).
+static V3 light_sample_box_from(const Primitive& p, V3 point, Fp x, Fp rnd_sign, Fp c1, Fp c2) {
+    V3 s = p.s;
+    Fp wx = 4.0 * s.y * s.z, wy = 4.0 * s.x * s.z;
+    V3 local;
+    if (x < wx) local = v3(s.x * rnd_sign, c1, c2);
+    else if (x < wx + wy) local = v3(c1, s.y * rnd_sign, c2);
+    else local = v3(c1, c2, s.z * rnd_sign);
+    return light_direction_from_local(p, point, local);
+}
+// [OWN SPEC] ellipsoid arm: local point = radii (.) (uniform point on the unit sphere).
+static V3 light_sample_ellipsoid_from(const Primitive& p, V3 point, V3 sphere_unit) { return light_direction_from_local(p, point, cmul(p.s, sphere_unit)); }
+
+// [REF] :83-125 DirectLightSamplingDistribution::sample_unit_vector with the reference's draw order per arm.
+static V3 direct_light_sample(const Primitive& p, V3 point, Rng* rng) {
+    if (p.kind == SHAPE_BOX) {
+        V3 s = p.s;
+        Fp wx = 4.0 * s.y * s.z, wy = 4.0 * s.x * s.z, wz = 4.0 * s.x * s.y;
+        Fp x = rng->gen_range(0.0, wx + wy + wz);
+        Fp rnd_sign = rng->gen_bool_half() ? 1.0 : -1.0;
+        Fp c1, c2;
+        if (x < wx) { c1 = rng->gen_range(-s.y, s.y); c2 = rng->gen_range(-s.z, s.z); }
+        else if (x < wx + wy) { c1 = rng->gen_range(-s.x, s.x); c2 = rng->gen_range(-s.z, s.z); }
+        else { c1 = rng->gen_range(-s.x, s.x); c2 = rng->gen_range(-s.y, s.y); }
+        return light_sample_box_from(p, point, x, rnd_sign, c1, c2);
+    }
+    if (p.kind == SHAPE_ELLIPSOID) {                                        // [OWN SPEC]: three normals -> unit sphere, like :55-61
+        Fp a = rng->normal(), b = rng->normal(), c = rng->normal();
+        return light_sample_ellipsoid_from(p, point, normalize(v3(a, b, c)));
+    }
+    Fp u = rng->gen_range01(), v = rng->gen_range01();
+    return light_sample_from_uv(p, point, u, v);
 }
 // :150-158 MultipleLightSamplingDistribution::sample_unit_vector
 static V3 multiple_light_sample(const Scene& sc, V3 point, Rng* rng) {
     size_t len = sc.bvh_light_sources.primitives.size();
     size_t idx = rng->gen_index(len);
-    Fp u = rng->gen_range01(), v = rng->gen_range01();
-    return light_sample_from_uv(sc.bvh_light_sources.primitives[idx], point, u, v);
+    return direct_light_sample(sc.bvh_light_sources.primitives[idx], point, rng);
 }
-// :160-184 MultipleLightSamplingDistribution::pdf
+// :160-184 MultipleLightSamplingDistribution::pdf: every hit of every pierced light contributes
+// local_pdf |p - point|^2 / |ng . omega| (both faces, no occlusion); the sum is divided by the light count.
 static Fp multiple_light_pdf(const Scene& sc, V3 point, V3 l, Counters* c) {
     Ray ray; ray.origin = point; ray.direction = l;
     std::vector<BvhIntersection> hits;
@@ -365,11 +576,14 @@ static Fp multiple_light_pdf(const Scene& sc, V3 point, V3 l, Counters* c) {
     Fp pdf = 0.0;
     for (const BvhIntersection& bi : hits) {
         Fp sum = 0.0;
-        V3 global = ray.origin + bi.hit.offset * ray.direction;
-        Fp local_pdf = get_local_pdf(*bi.primitive);
-        V3 vec = global - point;
-        V3 omega = normalize(vec);
-        sum += local_pdf * (norm_squared(vec) / std::fabs(dot(bi.hit.normal_geometry, omega)));
+        for (int k = 0; k < bi.n_hits; ++k) {
+            const Intersection& x = bi.hits[k];
+            V3 global = ray.origin + x.offset * ray.direction;
+            Fp local_pdf = get_local_pdf(*bi.primitive, bi.rotated_ray.origin + bi.rotated_ray.direction * x.offset);
+            V3 vec = global - point;
+            V3 omega = normalize(vec);
+            sum += local_pdf * (norm_squared(vec) / std::fabs(dot(x.normal_geometry, omega)));
+        }
         pdf += sum;
     }
     return pdf / (Fp)sc.bvh_light_sources.primitives.size();
@@ -492,23 +706,69 @@ static Ray primary_ray(const Scene& sc, int x, int y, Fp xi1, Fp xi2) {       //
     return r;
 }
 
+// [REF] rendering.rs:201-226 intersect_ray_with_scene: nearest BVH hit (first hit of the winning primitive), then a linear
+// scan of infinite_primitives with the running upper bound and strict `<`.
+static bool intersect_ray_with_scene(const Ray& ray, const Scene& sc, BvhIntersection* bi, Counters* c) {
+    Fp latest = FP_INF;
+    bool found = intersect_with_bvh_nearest_point(ray, sc.bvh_finite_primitives, bi, c);
+    if (found) latest = bi->hit.offset;
+    for (const Primitive& plane : sc.infinite_primitives) {
+        Intersection x;
+        ++c->tri_tests;
+        if (intersect_ray_with_object3d(ray, plane, latest, &x) && x.offset < latest) {
+            latest = x.offset; bi->hit = x; bi->hits[0] = x; bi->n_hits = 1; bi->primitive = &plane; bi->u = bi->v = 1.0 / 3.0; found = true;
+        }
+    }
+    return found;
+}
+
 static V3 get_ray_color(const Ray& ray, const Scene& sc, int depth, Rng* rng, Counters* c) {   // :86-127
     if (depth <= 0) return v3(0, 0, 0);
     BvhIntersection bi;
     ++c->segments;
-    if (!intersect_with_bvh_nearest_point(ray, sc.bvh_finite_primitives, &bi, c)) return sc.bg_color;   // :201-226 (infinite_primitives empty)
+    if (!intersect_ray_with_scene(ray, sc, &bi, c)) return sc.bg_color;       // :96, :125
     ++c->vertices;
     const Primitive& prim = *bi.primitive;
     V3 corrected_point = ray.origin + ray.direction * (bi.hit.offset - EPS);
     V3 total = prim.emission;
     V3 n = bi.hit.normal_geometry;
     V3 v = -normalize(ray.direction);
+    if (prim.mat_kind == MAT_DIELECTRIC) {
+        // [OWN SPEC] (reference HEAD has no transmissive material, only the dead fields `ior` scene.rs:18
+        // and `is_outer_to_inner` geometry.rs:23): smooth dielectric, delta BSDF, no rejection loop.  eta = n_from / n_to with
+        // the outside index 1; Schlick reflectance; total internal reflection reflects; one uniform picks reflection (< R) or
+        // refraction; the refracted ray starts EPS BEHIND the surface and is tinted by the base colour when it ENTERS.
+        ++c->attempts;
+        Fp eta = bi.hit.is_outer_to_inner ? 1.0 / prim.ior : prim.ior;
+        Fp cos1 = dot(n, v);
+        Fp sin2 = eta * std::sqrt(std::max(0.0, 1.0 - cos1 * cos1));
+        Fp u = rng->gen_f64();
+        bool reflect = true;
+        Fp cos2 = 0.0;
+        if (sin2 < 1.0) {
+            cos2 = std::sqrt(1.0 - sin2 * sin2);
+            Fp r0 = powi2((eta - 1.0) / (eta + 1.0));
+            Fp refl = r0 + (1.0 - r0) * powi5(1.0 - cos1);
+            reflect = u < refl;
+        }
+        Ray next; V3 weight = v3(1, 1, 1);
+        if (reflect) { next.origin = corrected_point; next.direction = normalize(reflect_vec(v, n)); }
+        else {
+            next.origin = ray.origin + ray.direction * (bi.hit.offset + EPS);
+            next.direction = normalize((-v) * eta + n * (eta * cos1 - cos2));
+            if (bi.hit.is_outer_to_inner) weight = prim.material.base_color_factor;
+        }
+        return total + cmul(get_ray_color(next, sc, depth - 1, rng, c), weight);
+    }
     V3 l; Fp pdf;
-    for (;;) {                                                                // rejection loop :102-110
+    for (int attempt = 1;; ++attempt) {                                       // rejection loop :102-110
         ++c->attempts;
         l = mix_sample(sc, corrected_point, n, v, prim.material, rng, c);
         pdf = mix_pdf(sc, corrected_point, n, l, v, prim.material, c);
         if (pdf > 0.0 && dot(l, bi.hit.normal_shading) > 0.0) break;
+        // the reference spins for ever when no direction can pass (e.g. an object rotated by ~180 degrees: normal_shading is
+        // not rotated back); sc.max_attempts > 0 ends the path like the device's attempt cap does (0 = unbounded, the reference)
+        if (sc.max_attempts > 0 && attempt >= sc.max_attempts) { ++c->attempt_cap_hits; return total; }
     }
     Ray next; next.origin = corrected_point; next.direction = l;
     V3 refl = get_ray_color(next, sc, depth - 1, rng, c);
@@ -549,9 +809,16 @@ struct OrSceneDesc {
     const double* tri_n;          // n x 9  (a_norm, b_norm, c_norm)
     const double* tri_material;   // n x 5  (base r g b, metallic, roughness)
     const double* tri_emission;   // n x 3
+    // general primitives (all may be null = triangles with identity transforms, what the glTF loader emits):
+    const int32_t* kind;          // n: SHAPE_* ; for kind != TRIANGLE the first 3 doubles of tri_v are s / radii / plane normal
+    const double* position;       // n x 3  Object3D.position
+    const double* rotation;       // n x 4  Object3D.rotation as (i, j, k, w)
+    const double* ior;            // n      Primitive.ior (scene.rs:18)
+    const int32_t* mat_kind;      // n: MAT_PBR | MAT_DIELECTRIC
+    int32_t max_attempts, _pad2;  // 0 = unbounded rejection loop (the reference)
 };
 struct OrInfo { int64_t n_nodes, n_leaves, depth, n_lights, n_light_nodes, validate_failures; };
-struct OrStats { uint64_t node_tests, tri_tests, segments, vertices, attempts, light_node_tests, light_tri_tests, vndf_assert_fail, nan_pixels, samples; double seconds; };
+struct OrStats { uint64_t node_tests, tri_tests, segments, vertices, attempts, light_node_tests, light_tri_tests, vndf_assert_fail, nan_pixels, samples; double seconds; uint64_t attempt_cap_hits; };
 
 static V3 rd3(const double* p) { return v3(p[0], p[1], p[2]); }
 static void wr3(double* p, V3 v) { p[0] = v.x; p[1] = v.y; p[2] = v.z; }
@@ -562,17 +829,28 @@ void* or_scene_create(const OrSceneDesc* d) {
     sc->bg_color = rd3(d->bg_color); sc->camera_position = rd3(d->camera_position); sc->camera_forward = rd3(d->camera_forward);
     sc->camera_right = rd3(d->camera_right); sc->camera_up = rd3(d->camera_up);
     sc->camera_fov_x = d->camera_fov_x; sc->camera_fov_y = d->camera_fov_y;
+    sc->max_attempts = d->max_attempts;
     std::vector<Primitive> finite, lights;
     for (int i = 0; i < d->n_tris; ++i) {
         Primitive p;
+        p.kind = d->kind ? d->kind[i] : SHAPE_TRIANGLE;
+        p.s = rd3(d->tri_v + 9 * i);
+        p.position = d->position ? rd3(d->position + 3 * i) : v3(0, 0, 0);
+        Quat q = {0, 0, 0, 1};
+        if (d->rotation) { q.i = d->rotation[4 * i]; q.j = d->rotation[4 * i + 1]; q.k = d->rotation[4 * i + 2]; q.w = d->rotation[4 * i + 3]; }
+        p.rotation = q;
+        p.identity = q.i == 0 && q.j == 0 && q.k == 0 && q.w == 1 && p.position.x == 0 && p.position.y == 0 && p.position.z == 0;
+        p.ior = d->ior ? d->ior[i] : 1.0;
+        p.mat_kind = d->mat_kind ? d->mat_kind[i] : MAT_PBR;
         p.a = rd3(d->tri_v + 9 * i); p.b = rd3(d->tri_v + 9 * i + 3); p.c = rd3(d->tri_v + 9 * i + 6);
         p.a_norm = rd3(d->tri_n + 9 * i); p.b_norm = rd3(d->tri_n + 9 * i + 3); p.c_norm = rd3(d->tri_n + 9 * i + 6);
         p.material.base_color_factor = rd3(d->tri_material + 5 * i);
         p.material.metallic_factor = d->tri_material[5 * i + 3];
         p.material.metallic_roughness = d->tri_material[5 * i + 4];
         p.emission = rd3(d->tri_emission + 3 * i);
-        p.aabb = calculate_aabb_for_object(p);                         // gltf_to_scene.rs:234
         p.orig_id = i;
+        if (p.kind == SHAPE_PLANE) { p.aabb = Aabb::empty(); sc->infinite_primitives.push_back(p); continue; }   // scene.rs:37; [OWN SPEC] planes are never lights
+        p.aabb = calculate_aabb_for_object(p);                         // gltf_to_scene.rs:234
         finite.push_back(p);
         if (norm(p.emission) > EPS) lights.push_back(p);               // gltf_to_scene.rs:240
     }
@@ -593,7 +871,7 @@ void or_scene_info(void* h, OrInfo* o) {
     const BvhTree& t = sc->bvh_finite_primitives;
     o->n_nodes = (int64_t)t.nodes.size(); o->n_leaves = 0;
     for (const BvhNode& n : t.nodes) if (n.left_child_index == NO_CHILD) ++o->n_leaves;
-    o->depth = tree_depth(t, t.nodes.size() - 1);
+    o->depth = t.nodes.empty() ? 0 : tree_depth(t, t.nodes.size() - 1);
     o->n_lights = (int64_t)sc->bvh_light_sources.primitives.size();
     o->n_light_nodes = (int64_t)sc->bvh_light_sources.nodes.size();
     o->validate_failures = validate_bvh(t) + validate_bvh(sc->bvh_light_sources);     // rendering.rs:22
@@ -675,15 +953,17 @@ int or_render(void* h, uint64_t seed, int n_threads, int y0, int y1, int y_step,
             stats->node_tests += c.node_tests; stats->tri_tests += c.tri_tests; stats->segments += c.segments; stats->vertices += c.vertices;
             stats->attempts += c.attempts; stats->light_node_tests += c.light_node_tests; stats->light_tri_tests += c.light_tri_tests;
             stats->vndf_assert_fail += c.vndf_assert_fail; stats->nan_pixels += c.nan_pixels; stats->samples += c.samples;
+            stats->attempt_cap_hits += c.attempt_cap_hits;
         }
         stats->seconds = std::chrono::duration<double>(t_end - t_begin).count();
     }
     return 0;
 }
 
-// Nearest hit of n rays (o[3], d[3] each) through the reference traversal.  tri_id = original (load-order)
-// triangle index or -1; t, u, v of the winner; second_t = nearest t among all OTHER triangles (brute force,
-// +inf if none) so callers can recognise ties (SURVEY.md 8d parity rule).
+// Nearest hit of n rays (o[3], d[3] each) through intersect_ray_with_scene (BVH, then the infinite primitives).
+// tri_id = original (load-order) primitive index or -1; t of the winner; (u, v) its barycentrics (1/3, 1/3 for shapes
+// without edges); second_t = nearest FIRST hit among all OTHER primitives (brute force, +inf if none) so callers can
+// recognise ties (SURVEY.md 8d parity rule).
 void or_trace_primary(void* h, const double* rays, int64_t n, int32_t* tri_id, double* t, double* u, double* v, double* second_t, OrStats* stats) {
     Scene* sc = (Scene*)h;
     Counters c; std::memset(&c, 0, sizeof(c));
@@ -691,33 +971,36 @@ void or_trace_primary(void* h, const double* rays, int64_t n, int32_t* tri_id, d
     for (int64_t i = 0; i < n; ++i) {
         Ray r; r.origin = rd3(rays + 6 * i); r.direction = rd3(rays + 6 * i + 3);
         BvhIntersection bi; ++c.segments;
-        bool hit = intersect_with_bvh_nearest_point(r, tree, &bi, &c);
+        bool hit = intersect_ray_with_scene(r, *sc, &bi, &c);
         tri_id[i] = hit ? bi.primitive->orig_id : -1;
         t[i] = hit ? bi.hit.offset : FP_INF;
         if (u) u[i] = hit ? bi.u : 0.0;
         if (v) v[i] = hit ? bi.v : 0.0;
         if (second_t) {
             Fp best = FP_INF;
-            for (const Primitive& p : tree.primitives) {
-                if (hit && p.orig_id == bi.primitive->orig_id) continue;
-                Intersection x;
-                if (intersect_with_triangle(r, FP_INF, p, &x) && x.offset < best) best = x.offset;
-            }
+            auto consider = [&](const Primitive& p) {
+                if (hit && p.orig_id == bi.primitive->orig_id) return;
+                Intersection x[2];
+                if (intersect_ray_with_object3d_all_points(r, p, x, nullptr) > 0 && x[0].offset < best) best = x[0].offset;
+            };
+            for (const Primitive& p : tree.primitives) consider(p);
+            for (const Primitive& p : sc->infinite_primitives) consider(p);
             second_t[i] = best;
         }
     }
     if (stats) { std::memset(stats, 0, sizeof(*stats)); stats->node_tests = c.node_tests; stats->tri_tests = c.tri_tests; stats->segments = c.segments; }
 }
 
-// Full hit record for n rays: t, ng[3], ns[3], orig id (as double) -> 8 doubles per ray (t = inf on miss).
+// Full hit record for n rays: t, ng[3], ns[3], orig id, is_outer_to_inner (as doubles) -> 9 doubles per ray (t = inf on miss).
 void or_trace_hits(void* h, const double* rays, int64_t n, double* out) {
     Scene* sc = (Scene*)h; Counters c; std::memset(&c, 0, sizeof(c));
     for (int64_t i = 0; i < n; ++i) {
         Ray r; r.origin = rd3(rays + 6 * i); r.direction = rd3(rays + 6 * i + 3);
-        BvhIntersection bi; double* o = out + 8 * i;
-        if (intersect_with_bvh_nearest_point(r, sc->bvh_finite_primitives, &bi, &c)) {
+        BvhIntersection bi; double* o = out + 9 * i;
+        if (intersect_ray_with_scene(r, *sc, &bi, &c)) {
             o[0] = bi.hit.offset; wr3(o + 1, bi.hit.normal_geometry); wr3(o + 4, bi.hit.normal_shading); o[7] = (double)bi.primitive->orig_id;
-        } else { o[0] = FP_INF; for (int k = 1; k < 7; ++k) o[k] = 0.0; o[7] = -1.0; }
+            o[8] = bi.hit.is_outer_to_inner ? 1.0 : 0.0;
+        } else { o[0] = FP_INF; for (int k = 1; k < 7; ++k) o[k] = 0.0; o[7] = -1.0; o[8] = 0.0; }
     }
 }
 
@@ -759,13 +1042,52 @@ void or_sample_vndf(const double* n, const double* v, const double* rough, const
 void or_sample_vndf_cap(const double* n, const double* v, const double* rough, const double* u12, int64_t cnt, double* out) {
     for (int64_t i = 0; i < cnt; ++i) wr3(out + 3 * i, vndf_cap_sample_from_u(rd3(n + 3 * i), rd3(v + 3 * i), rough[i], u12[2 * i], u12[2 * i + 1]));
 }
-// light_idx indexes the light list in LOAD order (ascending original triangle id).
-void or_sample_light(void* h, const int32_t* light_idx, const double* point, const double* uv, int64_t cnt, double* out) {
+// light_idx indexes the light list in LOAD order (ascending original primitive id).  draws: 4 doubles per sample --
+// triangle: (u, v, -, -); box: (x in [0,1) scaled by wx+wy+wz, sign +-1, c1, c2 in [-1,1) scaled by the face's half sizes);
+// ellipsoid: (sphere_unit xyz, -).
+void or_sample_light(void* h, const int32_t* light_idx, const double* point, const double* draws, int64_t cnt, double* out) {
     Scene* sc = (Scene*)h;
     std::vector<const Primitive*> by_load;
     for (const Primitive& p : sc->bvh_light_sources.primitives) by_load.push_back(&p);
     std::sort(by_load.begin(), by_load.end(), [](const Primitive* a, const Primitive* b) { return a->orig_id < b->orig_id; });
-    for (int64_t i = 0; i < cnt; ++i) wr3(out + 3 * i, light_sample_from_uv(*by_load[light_idx[i]], rd3(point + 3 * i), uv[2 * i], uv[2 * i + 1]));
+    for (int64_t i = 0; i < cnt; ++i) {
+        const Primitive& p = *by_load[light_idx[i]];
+        const double* q = draws + 4 * i;
+        V3 pt = rd3(point + 3 * i), l;
+        if (p.kind == SHAPE_BOX) {
+            V3 s = p.s;
+            Fp wx = 4.0 * s.y * s.z, wy = 4.0 * s.x * s.z, wz = 4.0 * s.x * s.y;
+            Fp x = q[0] * (wx + wy + wz);
+            Fp h1 = x < wx ? s.y : s.x, h2 = x < wx + wy ? s.z : s.y;
+            l = light_sample_box_from(p, pt, x, q[1], q[2] * h1, q[3] * h2);
+        } else if (p.kind == SHAPE_ELLIPSOID) l = light_sample_ellipsoid_from(p, pt, rd3(q));
+        else l = light_sample_from_uv(p, pt, q[0], q[1]);
+        wr3(out + 3 * i, l);
+    }
+}
+// Object-space intersection of one shape: kind, params (9 doubles like tri_v), ray -> n hits, per hit t, normal[3], outer flag (5 doubles).
+int or_intersect_shape(int32_t kind, const double* params, const double* o, const double* d, double upper, double* out10) {
+    Primitive p; std::memset(&p, 0, sizeof(p));
+    p.kind = kind; p.s = rd3(params); p.a = rd3(params); p.b = rd3(params + 3); p.c = rd3(params + 6);
+    V3 ng = cross(p.b - p.a, p.c - p.a); p.a_norm = p.b_norm = p.c_norm = ng;
+    p.identity = true; p.rotation = Quat{0, 0, 0, 1};
+    Ray r; r.origin = rd3(o); r.direction = rd3(d);
+    Intersection x[2];
+    int n = intersect_all_points(r, p, upper, x);
+    for (int k = 0; k < n; ++k) { out10[5 * k] = x[k].offset; wr3(out10 + 5 * k + 1, x[k].normal_geometry); out10[5 * k + 4] = x[k].is_outer_to_inner ? 1.0 : 0.0; }
+    return n;
+}
+void or_quat_transform(const double* q_ijkw, const double* v, int32_t conjugate, double* out) {
+    Quat q = {q_ijkw[0], q_ijkw[1], q_ijkw[2], q_ijkw[3]};
+    wr3(out, quat_transform(conjugate ? quat_conjugate(q) : q, rd3(v)));
+}
+// calculate_aabb_for_object (aabb.rs:75-94) of one primitive given like or_scene_create's arrays -> min[3], max[3].
+void or_object_aabb(int32_t kind, const double* params, const double* position, const double* q_ijkw, double* out6) {
+    Primitive p; std::memset(&p, 0, sizeof(p));
+    p.kind = kind; p.s = rd3(params); p.a = rd3(params); p.b = rd3(params + 3); p.c = rd3(params + 6);
+    p.position = rd3(position); p.rotation = Quat{q_ijkw[0], q_ijkw[1], q_ijkw[2], q_ijkw[3]}; p.identity = false;
+    Aabb a = calculate_aabb_for_object(p);
+    wr3(out6, a.min); wr3(out6 + 3, a.max);
 }
 void or_color_to_pixel(const double* rgb, int64_t cnt, uint8_t* out) { for (int64_t i = 0; i < cnt; ++i) color_to_pixel(rd3(rgb + 3 * i), out + 3 * i); }
 int or_intersect_triangle(const double* o, const double* d, const double* abc, double* tuv) {

@@ -23,9 +23,12 @@ CLI_PATH = os.path.join(_HERE, "_build", "raytracing-engine")
 HEADER_PATH = os.path.join(os.path.dirname(_HERE), "include", "rt_api.h")
 
 RT_OK, RT_ERR_INVALID, RT_ERR_IO, RT_ERR_FORMAT, RT_ERR_CUDA, RT_ERR_LIMIT = range(6)
-FN_BRDF, FN_PDF_COSINE, FN_PDF_VNDF, FN_PDF_LIGHT, FN_PDF_MIX, FN_SAMPLE_COSINE, FN_SAMPLE_VNDF, FN_SAMPLE_LIGHT, FN_PHILOX = range(1, 10)
+FN_BRDF, FN_PDF_COSINE, FN_PDF_VNDF, FN_PDF_LIGHT, FN_PDF_MIX, FN_SAMPLE_COSINE, FN_SAMPLE_VNDF, FN_SAMPLE_LIGHT, FN_PHILOX, FN_SAMPLE_LIGHT_GEN, FN_DIELECTRIC = range(1, 12)
 _FN_WIDTHS = {FN_BRDF: (14, 3), FN_PDF_COSINE: (6, 1), FN_PDF_VNDF: (10, 1), FN_PDF_LIGHT: (6, 1), FN_PDF_MIX: (13, 1),
-              FN_SAMPLE_COSINE: (5, 6), FN_SAMPLE_VNDF: (9, 3), FN_SAMPLE_LIGHT: (6, 3), FN_PHILOX: (4, 4)}
+              FN_SAMPLE_COSINE: (5, 6), FN_SAMPLE_VNDF: (9, 3), FN_SAMPLE_LIGHT: (6, 3), FN_PHILOX: (4, 4), FN_SAMPLE_LIGHT_GEN: (8, 3),
+              FN_DIELECTRIC: (9, 4)}
+SHAPE_TRIANGLE, SHAPE_BOX, SHAPE_ELLIPSOID, SHAPE_PLANE = range(4)
+MATERIAL_PBR, MATERIAL_DIELECTRIC = 0, 1
 
 _dp = C.POINTER(C.c_double)
 
@@ -47,10 +50,17 @@ class RtSceneDesc(C.Structure):
     ]
 
 
+_ip = C.POINTER(C.c_int32)
+
+
+class RtSceneDesc2(C.Structure):
+    _fields_ = [("base", RtSceneDesc), ("shape_kind", _ip), ("position", _dp), ("rotation", _dp), ("ior", _dp), ("material_kind", _ip)]
+
+
 class RtSceneInfo(C.Structure):
     _fields_ = [(k, C.c_int32) for k in ("n_tris", "n_lights", "n_materials", "n_nodes", "n_leaves", "bvh_depth", "max_leaf_size",
                                          "bvh_validate_failures", "scene_in_shared_memory", "device")] + [("device_bytes", C.c_int64)] + \
-               [("bvh_builder", C.c_int32), ("reserved1", C.c_int32), ("bvh_build_ms", C.c_double)]
+               [("bvh_builder", C.c_int32), ("reserved1", C.c_int32), ("bvh_build_ms", C.c_double), ("n_infinite", C.c_int32), ("general_primitives", C.c_int32)]
 
 
 class RtRenderParams(C.Structure):
@@ -94,7 +104,12 @@ def lib():
         L.rt_last_error.restype = C.c_char_p
         vp = C.c_void_p
         L.rt_scene_load_gltf.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+        L.rt_scene_load_text.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
+        L.rt_scene_load.argtypes = [C.c_char_p, C.c_int32, C.c_int32, C.c_int32, C.c_int32, C.POINTER(vp)]
         L.rt_scene_create.argtypes = [C.POINTER(RtSceneDesc), C.c_int32, C.POINTER(vp)]
+        L.rt_scene_create2.argtypes = [C.POINTER(RtSceneDesc2), C.c_int32, C.POINTER(vp)]
+        L.rt_scene_get_desc2.argtypes = [vp, C.POINTER(RtSceneDesc2)]
+        L.rt_trace_hits.argtypes = [vp, _dp, C.c_int64, _dp]
         L.rt_scene_destroy.argtypes = [vp]
         L.rt_scene_destroy.restype = None
         L.rt_scene_get_desc.argtypes = [vp, C.POINTER(RtSceneDesc)]
@@ -151,9 +166,26 @@ class Scene:
         return cls(h.value)
 
     @classmethod
+    def from_text(cls, path, width=0, height=0, samples=0, device=0):
+        """The course's text scene format (own spec: no parser at reference HEAD); 0 keeps the file's DIMENSIONS / SAMPLES."""
+        h = C.c_void_p()
+        _check(lib().rt_scene_load_text(os.fsencode(path), width, height, samples, device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
+    def from_file(cls, path, width=0, height=0, samples=0, device=0):
+        h = C.c_void_p()
+        _check(lib().rt_scene_load(os.fsencode(path), width, height, samples, device, C.byref(h)))
+        return cls(h.value)
+
+    @classmethod
     def from_arrays(cls, *, width, height, samples, ray_depth, bg_color, camera_position, camera_forward, camera_right, camera_up,
-                    camera_fov_x, camera_fov_y, tri_v, tri_n, tri_material, tri_emission, device=0):
-        d = RtSceneDesc()
+                    camera_fov_x, camera_fov_y, tri_v, tri_n, tri_material, tri_emission, device=0,
+                    shape_kind=None, position=None, rotation=None, ior=None, material_kind=None):
+        """rt_scene_create, or rt_scene_create2 when any general-primitive array (shape_kind, position, rotation (i,j,k,w), ior,
+        material_kind) is given."""
+        d2 = RtSceneDesc2()
+        d = d2.base
         d.width, d.height, d.samples, d.ray_depth = width, height, samples, ray_depth
         for name, val in (("bg_color", bg_color), ("camera_position", camera_position), ("camera_forward", camera_forward),
                           ("camera_right", camera_right), ("camera_up", camera_up)):
@@ -163,8 +195,29 @@ class Scene:
         d.n_tris = int(arrs[0].size // 9)
         d.tri_v, d.tri_n, d.tri_material, d.tri_emission = (a.ctypes.data_as(_dp) for a in arrs)
         h = C.c_void_p()
-        _check(lib().rt_scene_create(C.byref(d), device, C.byref(h)))
+        if all(a is None for a in (shape_kind, position, rotation, ior, material_kind)):
+            _check(lib().rt_scene_create(C.byref(d), device, C.byref(h)))
+            return cls(h.value)
+        keep = []
+        for name, val, dt, pt in (("shape_kind", shape_kind, np.int32, _ip), ("position", position, np.float64, _dp), ("rotation", rotation, np.float64, _dp),
+                                  ("ior", ior, np.float64, _dp), ("material_kind", material_kind, np.int32, _ip)):
+            if val is not None:
+                a = np.ascontiguousarray(val, dtype=dt)
+                keep.append(a)
+                setattr(d2, name, a.ctypes.data_as(pt))
+        _check(lib().rt_scene_create2(C.byref(d2), device, C.byref(h)))
         return cls(h.value)
+
+    @classmethod
+    def from_flat(cls, fl, device=0, **over):
+        """From an object with the FlatScene attribute names (oracle.FlatScene; tests only -- this module never imports oracle)."""
+        kw = dict(width=fl.width, height=fl.height, samples=fl.samples, ray_depth=fl.ray_depth, bg_color=fl.bg_color, camera_position=fl.camera_position,
+                  camera_forward=fl.camera_forward, camera_right=fl.camera_right, camera_up=fl.camera_up, camera_fov_x=fl.camera_fov_x,
+                  camera_fov_y=fl.camera_fov_y, tri_v=fl.tri_v, tri_n=fl.tri_n, tri_material=fl.tri_material, tri_emission=fl.tri_emission,
+                  shape_kind=getattr(fl, "kind", None), position=getattr(fl, "position", None), rotation=getattr(fl, "rotation", None),
+                  ior=getattr(fl, "ior", None), material_kind=getattr(fl, "mat_kind", None), device=device)
+        kw.update(over)
+        return cls.from_arrays(**kw)
 
     def close(self):
         if self._h:
@@ -179,8 +232,9 @@ class Scene:
 
     # -- inspection ---------------------------------------------------------------------------------------------
     def desc(self) -> dict:
-        d = RtSceneDesc()
-        _check(lib().rt_scene_get_desc(self._h, C.byref(d)))
+        d2 = RtSceneDesc2()
+        _check(lib().rt_scene_get_desc2(self._h, C.byref(d2)))
+        d = d2.base
         n = d.n_tris
 
         def arr(p, w):
@@ -189,6 +243,9 @@ class Scene:
         for k in ("bg_color", "camera_position", "camera_forward", "camera_right", "camera_up"):
             out[k] = np.array(list(getattr(d, k)))
         out.update(tri_v=arr(d.tri_v, 9), tri_n=arr(d.tri_n, 9), tri_material=arr(d.tri_material, 5), tri_emission=arr(d.tri_emission, 3))
+        if d2.shape_kind:                                   # general-primitive scene
+            out.update(shape_kind=np.ctypeslib.as_array(d2.shape_kind, shape=(n,)).copy(), position=arr(d2.position, 3), rotation=arr(d2.rotation, 4),
+                       ior=np.ctypeslib.as_array(d2.ior, shape=(n,)).copy(), material_kind=np.ctypeslib.as_array(d2.material_kind, shape=(n,)).copy())
         return out
 
     def info(self) -> dict:
@@ -255,6 +312,13 @@ class Scene:
         _check(lib().rt_trace_primary(self._h, rays.ctypes.data_as(_dp), n, precision, tid.ctypes.data_as(C.POINTER(C.c_int32)), t.ctypes.data_as(_dp)))
         return tid, t
 
+    def trace_hits(self, rays):
+        """(n, 9): t, normal_geometry xyz, normal_shading xyz (normalised, object space), original primitive id, is_outer_to_inner."""
+        rays = np.ascontiguousarray(rays, dtype=np.float64)
+        out = np.zeros((rays.shape[0], 9), dtype=np.float64)
+        _check(lib().rt_trace_hits(self._h, rays.ctypes.data_as(_dp), rays.shape[0], out.ctypes.data_as(_dp)))
+        return out
+
     def primary_rays(self, xy, xi):
         xy = np.ascontiguousarray(xy, dtype=np.int32)
         xi = np.ascontiguousarray(xi, dtype=np.float64)
@@ -289,6 +353,11 @@ def measure_fp32_peak(device=0):
 # ---- the reference's call sequence (main.rs:45-67) ------------------------------------------------------------
 def convert_gltf_to_scene(path, width, height, samples, device=0) -> Scene:
     return Scene.from_gltf(path, width, height, samples, device)
+
+
+def parse_file_content(path, width=0, height=0, samples=0, device=0) -> Scene:
+    """main.rs:48 `// let scene = parse_file_content(file_lines);` -- the text-scene entry the reference dropped before HEAD."""
+    return Scene.from_text(path, width, height, samples, device)
 
 
 def render_scene(scene: Scene, seed: int = 0) -> np.ndarray:

@@ -30,20 +30,12 @@ struct Box {
 
 struct TempNode { Box box; int left = -1, right = -1, first = 0, count = 0; };
 
-Box tri_box(const double* v) {  // aabb.rs:53-65: min/max of the vertices -/+ EPS
-    Box b;
-    for (int a = 0; a < 3; ++a) {
-        b.mn[a] = std::min(std::min(v[a], v[3 + a]), v[6 + a]) - kEps;
-        b.mx[a] = std::max(std::max(v[a], v[3 + a]), v[6 + a]) + kEps;
-    }
-    return b;
-}
+Box from_d(const BoxD& d) { Box b; for (int a = 0; a < 3; ++a) { b.mn[a] = d.mn[a]; b.mx[a] = d.mx[a]; } return b; }
 
 float round_down(double x) { float f = (float)x; if ((double)f > x) f = std::nextafterf(f, -std::numeric_limits<float>::infinity()); return f; }
 float round_up(double x) { float f = (float)x; if ((double)f < x) f = std::nextafterf(f, std::numeric_limits<float>::infinity()); return f; }
 
 struct Build {
-    const double* tri_v;
     const BvhBuildParams& p;
     std::vector<Box> boxes;        // per original triangle id (only those in `order` are valid)
     std::vector<int32_t> order;    // being permuted
@@ -124,13 +116,29 @@ int emit(const Build& b, int t, FlatBvh* out) {
 
 }  // namespace
 
-void build_bvh(const double* tri_v, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out) {
+BoxD tri_box_d(const double* v) {  // aabb.rs:53-65: min/max of the vertices -/+ EPS
+    BoxD b;
+    for (int a = 0; a < 3; ++a) {
+        b.mn[a] = std::min(std::min(v[a], v[3 + a]), v[6 + a]) - kEps;
+        b.mx[a] = std::max(std::max(v[a], v[3 + a]), v[6 + a]) + kEps;
+    }
+    return b;
+}
+
+void quat_to_matrix(const double* q, double* m) {
+    const double i = q[0], j = q[1], k = q[2], w = q[3];
+    m[0] = 1 - 2 * (j * j + k * k); m[1] = 2 * (i * j - k * w);     m[2] = 2 * (i * k + j * w);
+    m[3] = 2 * (i * j + k * w);     m[4] = 1 - 2 * (i * i + k * k); m[5] = 2 * (j * k - i * w);
+    m[6] = 2 * (i * k - j * w);     m[7] = 2 * (j * k + i * w);     m[8] = 1 - 2 * (i * i + j * j);
+}
+
+void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out) {
     *out = FlatBvh();
-    Build b{tri_v, p, {}, ids, {}, {}};
+    Build b{p, {}, ids, {}, {}};
     int32_t max_id = -1;
     for (int32_t id : ids) max_id = std::max(max_id, id);
     b.boxes.resize((size_t)(max_id + 1));
-    for (int32_t id : ids) b.boxes[(size_t)id] = tri_box(tri_v + (size_t)id * 9);
+    for (int32_t id : ids) b.boxes[(size_t)id] = from_d(boxes[(size_t)id]);
     int max_depth = 0;
     if (!ids.empty()) b.build(0, (int)ids.size(), 1, &max_depth);
     out->tri_order = b.order;
@@ -155,7 +163,7 @@ void build_bvh(const double* tri_v, const std::vector<int32_t>& ids, const BvhBu
     }
 }
 
-int validate_flat_bvh(const FlatBvh& bvh, const double* tri_v) {
+int validate_flat_bvh(const FlatBvh& bvh, const std::vector<BoxD>& boxes) {
     int bad = 0;
     auto slot_box = [&bvh](int node, int s, float mn[3], float mx[3]) {
         const float* A = &bvh.box_a[(size_t)node * 4]; const float* B = &bvh.box_b[(size_t)node * 4]; const float* C = &bvh.box_c[(size_t)node * 4];
@@ -172,7 +180,7 @@ int validate_flat_bvh(const FlatBvh& bvh, const double* tri_v) {
                 uint32_t code = (uint32_t)~ref; int first = (int)(code >> 3), count = (int)(code & 7u) + 1;
                 if (bvh.tri_order.empty()) continue;
                 for (int i = first; i < first + count; ++i) {
-                    Box tb = tri_box(tri_v + (size_t)bvh.tri_order[(size_t)i] * 9);
+                    Box tb = from_d(boxes[(size_t)bvh.tri_order[(size_t)i]]);
                     for (int a = 0; a < 3; ++a) if (!((double)mn[a] <= tb.mn[a] && (double)mx[a] >= tb.mx[a])) { ++bad; break; }
                 }
             } else {

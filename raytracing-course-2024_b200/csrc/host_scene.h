@@ -16,14 +16,29 @@ struct HostScene {
     std::vector<double> tri_n;         // n x 9
     std::vector<double> tri_material;  // n x 5  (base rgb, metallic, roughness)
     std::vector<double> tri_emission;  // n x 3
-    int32_t n_tris() const { return (int32_t)(tri_v.size() / 9); }
+    // General primitives (Object3D + Shape3D::Box, geometry.rs:27-46; text-scene shapes and the dielectric material: own spec).
+    // All empty = every primitive is a world-space triangle with the metallic-roughness material (what the glTF loader emits).
+    // For kind != triangle the first three doubles of the tri_v row are the box half sizes / ellipsoid radii / plane normal.
+    std::vector<int32_t> kind;         // n: RT_SHAPE_*
+    std::vector<double> position;      // n x 3
+    std::vector<double> rotation;      // n x 4: unit quaternion (i, j, k, w)
+    std::vector<double> ior;           // n
+    std::vector<int32_t> mat_kind;     // n: RT_MATERIAL_*
+    int32_t n_tris() const { return (int32_t)(tri_v.size() / 9); }   // number of primitives of any kind
+    bool general() const { return !kind.empty(); }
 };
+
+// 3x3 rotation matrix (row major) of a unit quaternion (i, j, k, w): nalgebra UnitQuaternion::transform_vector as a matrix.
+void quat_to_matrix(const double* q, double* m9);
 
 // Loader status: ok, or a message + an RT_ERR_* class.
 struct LoadError { int code = 0; std::string message; };
 
 // main.rs:45-47: gltf::import(path) + convert_gltf_to_scene(..., width, height, samples).
 bool load_gltf_scene(const std::string& path, int32_t width, int32_t height, int32_t samples, HostScene* out, LoadError* err);
+// The course's text scene format (text_loader.cpp; no parser exists at reference HEAD -- own spec).
+// width / height / samples > 0 override DIMENSIONS / SAMPLES.
+bool load_text_scene(const std::string& path, int32_t width, int32_t height, int32_t samples, HostScene* out, LoadError* err);
 
 // ---- flattened device-layout BVH (built on the host, bvh_builder.cpp) ---------------------------------------
 // Binary BVH stored as "child-pair" nodes: inner node i keeps the boxes of BOTH children, so one visit tests two
@@ -40,13 +55,17 @@ struct FlatBvh {
     int32_t n_nodes = 0, n_leaves = 0, depth = 0, max_leaf = 0;
 };
 
+struct BoxD { double mn[3], mx[3]; };
+// aabb.rs:53-65 for a triangle: min/max of the vertices -/+ EPS.
+BoxD tri_box_d(const double* v9);
+
 struct BvhBuildParams {
     int max_leaf_size = 4;       // bvh.rs:89 (n <= 4 never splits)
     double traversal_cost = 1.0; // cost of one box test relative to one triangle test in the SAH
 };
 
-// tri_v: n x 9 doubles (load order); ids: which triangles to include (all, or the lights).
-void build_bvh(const double* tri_v, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out);
+// boxes: per primitive id (load order), EPS-padded like aabb.rs:53-94; ids: which primitives to include (the finite ones, or the lights).
+void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out);
 // GPU builder (rt_bvh_gpu.cu): Morton codes + radix sort + Karras hierarchy + refit + collapse to leaves <= max_leaf_size.
 // Same output format; lower tree quality than the SAH sweep, milliseconds instead of seconds on large meshes.  Returns
 // false (with *err) when CUDA fails or the set is too small to bother (<= 2 * max_leaf_size triangles).
@@ -54,6 +73,6 @@ bool build_bvh_gpu(const double* tri_v, int n_total_tris, const std::vector<int3
                    double* build_ms, std::string* err);
 // validate_bvh (bvh.rs:299-322) on the flattened tree: every leaf box contains its triangles' EPS-padded
 // boxes, every inner pair box contains the boxes stored in the child node.  Returns the number of violations.
-int validate_flat_bvh(const FlatBvh& bvh, const double* tri_v);
+int validate_flat_bvh(const FlatBvh& bvh, const std::vector<BoxD>& boxes);
 
 }  // namespace rtb

@@ -36,6 +36,7 @@ struct RtScene {
     rtb::FlatBvh bvh, light_bvh;
     std::vector<int32_t> light_ids;        // load order ids of emissive triangles (gltf_to_scene.rs:240)
     std::vector<int32_t> light_order;      // device order of the lights -> original id
+    std::vector<int32_t> plane_ids;        // load-order ids of the infinite primitives (scene.rs:37)
     rtd::SceneLayout L;
     std::vector<char> blob_host;
     std::vector<double> tri_d_host;        // BVH-ordered a, e1, e2 in f64 (precision-64 queries)
@@ -141,10 +142,68 @@ std::vector<float> octant_nodes(const rtb::FlatBvh& b) {
 int env_int(const char* name, int dflt) { const char* v = std::getenv(name); return v && *v ? std::atoi(v) : dflt; }
 double env_double(const char* name, double dflt) { const char* v = std::getenv(name); return v && *v ? std::atof(v) : dflt; }
 
+// World-space vertices of triangle i: q * v + position for a general scene (the reference rotates the RAY into object space
+// instead, geometry.rs:201-214 -- the same hit at the same t), the stored vertices otherwise.
+void world_triangle(const rtb::HostScene& h, int i, double* v9) {
+    const double* v = &h.tri_v[(size_t)i * 9];
+    if (!h.general()) { for (int k = 0; k < 9; ++k) v9[k] = v[k]; return; }
+    double m[9];
+    rtb::quat_to_matrix(&h.rotation[(size_t)i * 4], m);
+    const double* p = &h.position[(size_t)i * 3];
+    for (int c = 0; c < 3; ++c)
+        for (int a = 0; a < 3; ++a) v9[c * 3 + a] = m[a * 3] * v[c * 3] + m[a * 3 + 1] * v[c * 3 + 1] + m[a * 3 + 2] * v[c * 3 + 2] + p[a];
+}
+
+// calculate_aabb_for_object (aabb.rs:53-94): triangles: padded bounds of the (world-space) vertices; boxes / ellipsoids: bounds
+// of the 8 rotated + translated corners of the EPS-padded object-space box +-(s + EPS).
+rtb::BoxD object_box(const rtb::HostScene& h, int i) {
+    const int kind = h.general() ? h.kind[(size_t)i] : RT_SHAPE_TRIANGLE;
+    if (kind == RT_SHAPE_TRIANGLE) { double v[9]; world_triangle(h, i, v); return rtb::tri_box_d(v); }
+    double m[9];
+    rtb::quat_to_matrix(&h.rotation[(size_t)i * 4], m);
+    const double* p = &h.position[(size_t)i * 3];
+    const double* s = &h.tri_v[(size_t)i * 9];
+    rtb::BoxD b;
+    for (int a = 0; a < 3; ++a) { b.mn[a] = std::numeric_limits<double>::infinity(); b.mx[a] = -b.mn[a]; }
+    for (int c = 0; c < 8; ++c) {
+        const double x = ((c & 1) ? 1.0 : -1.0) * (s[0] + kEps), y = ((c & 2) ? 1.0 : -1.0) * (s[1] + kEps), z = ((c & 4) ? 1.0 : -1.0) * (s[2] + kEps);
+        for (int a = 0; a < 3; ++a) {
+            const double w = m[a * 3] * x + m[a * 3 + 1] * y + m[a * 3 + 2] * z + p[a];
+            b.mn[a] = std::min(b.mn[a], w); b.mx[a] = std::max(b.mx[a], w);
+        }
+    }
+    return b;
+}
+
+// 64-byte device record of primitive i of a general scene (rt_device.cuh "general primitives").
+void prim_record(const rtb::HostScene& h, int i, float* out16) {
+    const int kind = h.kind[(size_t)i];
+    if (kind == RT_SHAPE_TRIANGLE) {
+        double v[9]; world_triangle(h, i, v);
+        float rec[12];
+        tri_test_record(v, rec);
+        double e1[3], e2[3];
+        for (int a = 0; a < 3; ++a) { e1[a] = v[3 + a] - v[a]; e2[a] = v[6 + a] - v[a]; }
+        const double nu[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
+        const double area = 0.5 * std::sqrt(nu[0] * nu[0] + nu[1] * nu[1] + nu[2] * nu[2]);
+        for (int q = 0; q < 4; ++q) for (int a = 0; a < 3; ++a) out16[q * 4 + a] = rec[q * 3 + a];
+        out16[3] = i2f(RT_SHAPE_TRIANGLE); out16[7] = (float)(1.0 / area); out16[11] = 0.f; out16[15] = 0.f;   // 1/area: get_local_pdf distributions.rs:76-79
+        return;
+    }
+    double m[9];
+    rtb::quat_to_matrix(&h.rotation[(size_t)i * 4], m);
+    const double* p = &h.position[(size_t)i * 3];
+    const double* s = &h.tri_v[(size_t)i * 9];
+    for (int r = 0; r < 3; ++r) for (int a = 0; a < 3; ++a) out16[r * 4 + a] = (float)m[a * 3 + r];   // rows of R^T = columns of R
+    for (int a = 0; a < 3; ++a) out16[12 + a] = (float)p[a];
+    out16[3] = i2f(kind); out16[7] = (float)s[0]; out16[11] = (float)s[1]; out16[15] = (float)s[2];
+}
+
 // Flatten the host scene into the device blob (rt_device.cuh SceneLayout).
 int flatten_scene(RtScene* s) {
     const rtb::HostScene& h = s->host;
-    const int n = h.n_tris();
+    const bool gen = h.general();
+    const int n_all = h.n_tris();
     rtb::BvhBuildParams bp;
     // measured on B200 (tools/sweep.py): leaves of <= 2 triangles (tested side by side by the kernel) and a box test priced at
     // 2 triangle tests give the fastest trees; the reference's own limit is 4 (bvh.rs:89)
@@ -152,13 +211,21 @@ int flatten_scene(RtScene* s) {
     bp.traversal_cost = env_double("RT_BVH_TRAV_COST", 2.0);
     if (bp.max_leaf_size < 1) bp.max_leaf_size = 1;
     if (bp.max_leaf_size > 8) bp.max_leaf_size = 8;
-    std::vector<int32_t> all((size_t)n);
-    for (int i = 0; i < n; ++i) all[(size_t)i] = i;
+    // finite primitives -> BVH (scene.rs:33); planes -> infinite_primitives (scene.rs:37)
+    std::vector<int32_t> all;
+    s->plane_ids.clear();
+    for (int i = 0; i < n_all; ++i) {
+        if (gen && h.kind[(size_t)i] == RT_SHAPE_PLANE) s->plane_ids.push_back(i);
+        else all.push_back(i);
+    }
+    const int n = (int)all.size(), n_planes = (int)s->plane_ids.size();
+    std::vector<rtb::BoxD> boxes((size_t)n_all);
+    for (int32_t id : all) boxes[(size_t)id] = object_box(h, id);
     // builder: host SAH sweep (default: best trees) or the GPU LBVH builder (RT_BVH_BUILDER=gpu: fastest scene load)
     const char* which = std::getenv("RT_BVH_BUILDER");
     s->bvh_builder = 0; s->bvh_build_ms = 0.0;
     bool built = false;
-    if (which && std::strcmp(which, "gpu") == 0 && s->device >= 0) {
+    if (which && std::strcmp(which, "gpu") == 0 && s->device >= 0 && !gen) {
         std::string gerr;
         rtb::BvhBuildParams gp = bp;
         if (!std::getenv("RT_BVH_MAX_LEAF")) gp.max_leaf_size = 4;           // LBVH subtrees collapse into leaves of <= 4
@@ -167,22 +234,22 @@ int flatten_scene(RtScene* s) {
     }
     if (!built) {
         const auto t0 = std::chrono::steady_clock::now();
-        rtb::build_bvh(h.tri_v.data(), all, bp, &s->bvh);
+        rtb::build_bvh(boxes, all, bp, &s->bvh);
         s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
-    s->validate_failures = rtb::validate_flat_bvh(s->bvh, h.tri_v.data());
+    s->validate_failures = rtb::validate_flat_bvh(s->bvh, boxes);
 
-    // lights: emission.norm() > EPS (gltf_to_scene.rs:240)
+    // lights: emission.norm() > EPS (gltf_to_scene.rs:240), finite primitives only
     s->light_ids.clear();
-    for (int i = 0; i < n; ++i) {
+    for (int32_t i : all) {
         const double* e = &h.tri_emission[(size_t)i * 3];
         if (std::sqrt(e[0] * e[0] + e[1] * e[1] + e[2] * e[2]) > kEps) s->light_ids.push_back(i);
     }
     const int n_lights = (int)s->light_ids.size();
     const bool use_light_bvh = n_lights > RT_BRUTE_LIGHTS;
     if (use_light_bvh) {
-        rtb::build_bvh(h.tri_v.data(), s->light_ids, bp, &s->light_bvh);
-        s->validate_failures += rtb::validate_flat_bvh(s->light_bvh, h.tri_v.data());
+        rtb::build_bvh(boxes, s->light_ids, bp, &s->light_bvh);
+        s->validate_failures += rtb::validate_flat_bvh(s->light_bvh, boxes);
         s->light_order = s->light_bvh.tri_order;
     } else {
         s->light_bvh = rtb::FlatBvh();
@@ -191,62 +258,79 @@ int flatten_scene(RtScene* s) {
 
     // materials: per-primitive in the reference (scene.rs:13-20); deduplicated by value for the device table
     std::map<std::vector<double>, int> mat_index;
-    std::vector<float> mat0, mat1;
-    std::vector<int32_t> tri_mat((size_t)n);
-    for (int i = 0; i < n; ++i) {
-        std::vector<double> key(8);
+    std::vector<float> mat0, mat1, mat2;
+    std::vector<int32_t> tri_mat((size_t)n_all);
+    bool has_dielectric = false;
+    for (int i = 0; i < n_all; ++i) {
+        std::vector<double> key(10, 0.0);
         for (int k = 0; k < 5; ++k) key[(size_t)k] = h.tri_material[(size_t)i * 5 + (size_t)k];
         for (int k = 0; k < 3; ++k) key[(size_t)(5 + k)] = h.tri_emission[(size_t)i * 3 + (size_t)k];
+        key[8] = gen ? h.ior[(size_t)i] : 1.0; key[9] = gen ? (double)h.mat_kind[(size_t)i] : 0.0;
+        if (key[9] == (double)RT_MATERIAL_DIELECTRIC) has_dielectric = true;
         auto it = mat_index.find(key);
         if (it == mat_index.end()) {
             int id = (int)mat_index.size();
             mat_index[key] = id;
             mat0.insert(mat0.end(), {(float)key[0], (float)key[1], (float)key[2], (float)key[3]});
             mat1.insert(mat1.end(), {(float)key[5], (float)key[6], (float)key[7], (float)key[4]});
+            mat2.insert(mat2.end(), {(float)key[8], i2f((int32_t)key[9]), 0.f, 0.f});
             tri_mat[(size_t)i] = id;
         } else tri_mat[(size_t)i] = it->second;
     }
-    if (mat0.empty()) { mat0.assign(4, 0.f); mat1.assign(4, 0.f); }
+    if (mat0.empty()) { mat0.assign(4, 0.f); mat1.assign(4, 0.f); mat2.assign(4, 0.f); }
     s->n_mats = (int)mat_index.size();
 
-    // BVH-ordered triangle + shading arrays
-    const int nt = n > 0 ? n : 1;   // an empty scene keeps one degenerate triangle (never hit: det == 0)
+    // device order of the primitives: the finite ones in BVH order, then the planes
+    std::vector<int32_t> dev_order = s->bvh.tri_order;
+    dev_order.insert(dev_order.end(), s->plane_ids.begin(), s->plane_ids.end());
+    const int n_dev = (int)dev_order.size();
+    const int nt = n_dev > 0 ? n_dev : 1;   // an empty scene keeps one degenerate triangle (never hit: det == 0)
     std::vector<float> tri_a((size_t)nt * 4, 0.f), tri_e1((size_t)nt * 4, 0.f), tri_e2((size_t)nt * 4, 0.f);
-    std::vector<float> tri_t((size_t)nt * 12, std::numeric_limits<float>::quiet_NaN());
+    std::vector<float> tri_t((size_t)(gen ? 1 : nt) * 12, std::numeric_limits<float>::quiet_NaN());
+    std::vector<float> prims((size_t)(gen ? nt : 1) * 16, std::numeric_limits<float>::quiet_NaN());
     std::vector<float> sh_n0((size_t)nt * 4, 0.f), sh_dn1((size_t)nt * 4, 0.f), sh_dn2((size_t)nt * 4, 0.f), sh_ng((size_t)nt * 4, 0.f);
     s->tri_d_host.assign((size_t)nt * 9, 0.0);
     sh_dn1[3] = i2f(-1);
-    for (int k = 0; k < n; ++k) {
-        const int id = s->bvh.tri_order[(size_t)k];
-        const double* v = &h.tri_v[(size_t)id * 9];
+    if (gen && n_dev == 0) prims[3] = i2f(RT_SHAPE_TRIANGLE);      // the degenerate filler: NaN triangle, never hit
+    for (int k = 0; k < n_dev; ++k) {
+        const int id = dev_order[(size_t)k];
+        sh_n0[(size_t)k * 4 + 3] = i2f(tri_mat[(size_t)id]);
+        sh_dn1[(size_t)k * 4 + 3] = i2f(id);
+        if (gen) prim_record(h, id, &prims[(size_t)k * 16]);
+        if (gen && h.kind[(size_t)id] != RT_SHAPE_TRIANGLE) continue;
+        double v[9];
+        world_triangle(h, id, v);
         const double* nn = &h.tri_n[(size_t)id * 9];
         double e1[3], e2[3];
         for (int a = 0; a < 3; ++a) { e1[a] = v[3 + a] - v[a]; e2[a] = v[6 + a] - v[a]; }
         double ng[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
         const double len = std::sqrt(ng[0] * ng[0] + ng[1] * ng[1] + ng[2] * ng[2]);
-        tri_test_record(v, &tri_t[(size_t)k * 12]);
+        if (!gen) tri_test_record(v, &tri_t[(size_t)k * 12]);
         for (int a = 0; a < 3; ++a) {
             tri_a[(size_t)k * 4 + (size_t)a] = (float)v[a];
             tri_e1[(size_t)k * 4 + (size_t)a] = (float)e1[a];
             tri_e2[(size_t)k * 4 + (size_t)a] = (float)e2[a];
-            sh_n0[(size_t)k * 4 + (size_t)a] = (float)nn[a];
-            sh_dn1[(size_t)k * 4 + (size_t)a] = (float)(nn[3 + a] - nn[a]);
+            sh_n0[(size_t)k * 4 + (size_t)a] = (float)nn[a];                       // general scenes: OBJECT-space normals (normal_shading is
+            sh_dn1[(size_t)k * 4 + (size_t)a] = (float)(nn[3 + a] - nn[a]);        // not rotated back, geometry.rs:245-249)
             sh_dn2[(size_t)k * 4 + (size_t)a] = (float)(nn[6 + a] - nn[a]);
             sh_ng[(size_t)k * 4 + (size_t)a] = (float)(ng[a] / len);
             s->tri_d_host[(size_t)k * 9 + (size_t)a] = v[a];
             s->tri_d_host[(size_t)k * 9 + 3 + (size_t)a] = e1[a];
             s->tri_d_host[(size_t)k * 9 + 6 + (size_t)a] = e2[a];
         }
-        sh_n0[(size_t)k * 4 + 3] = i2f(tri_mat[(size_t)id]);
-        sh_dn1[(size_t)k * 4 + 3] = i2f(id);
     }
     // light arrays (device light order)
     const int nl = n_lights > 0 ? n_lights : 1;
     std::vector<float> lt_a((size_t)nl * 4, 0.f), lt_e1((size_t)nl * 4, 0.f), lt_e2((size_t)nl * 4, 0.f);
     std::vector<float> lt_t((size_t)nl * 16, std::numeric_limits<float>::quiet_NaN());
+    std::vector<float> lt_g((size_t)(gen ? nl : 1) * 16, std::numeric_limits<float>::quiet_NaN());
+    if (gen) lt_g[3] = i2f(RT_SHAPE_TRIANGLE);
     for (int k = 0; k < n_lights; ++k) {
         const int id = s->light_order[(size_t)k];
-        const double* v = &h.tri_v[(size_t)id * 9];
+        if (gen) prim_record(h, id, &lt_g[(size_t)k * 16]);
+        if (gen && h.kind[(size_t)id] != RT_SHAPE_TRIANGLE) continue;
+        double v[9];
+        world_triangle(h, id, v);
         double e1[3], e2[3];
         for (int a = 0; a < 3; ++a) { e1[a] = v[3 + a] - v[a]; e2[a] = v[6 + a] - v[a]; }
         double ng[3] = {e1[1] * e2[2] - e1[2] * e2[1], e1[2] * e2[0] - e1[0] * e2[2], e1[0] * e2[1] - e1[1] * e2[0]};
@@ -270,6 +354,7 @@ int flatten_scene(RtScene* s) {
     const std::vector<float> nodes = octant_nodes(s->bvh);
     L.nodes = w.add(nodes.data(), nodes.size() * 4);
     L.tri_t = w.add(tri_t.data(), tri_t.size() * 4);
+    if (gen) L.prims = w.add(prims.data(), prims.size() * 4);
     L.tri_a = w.add(tri_a.data(), tri_a.size() * 4);
     L.tri_e1 = w.add(tri_e1.data(), tri_e1.size() * 4);
     L.tri_e2 = w.add(tri_e2.data(), tri_e2.size() * 4);
@@ -279,19 +364,24 @@ int flatten_scene(RtScene* s) {
     L.sh_ng = w.add(sh_ng.data(), sh_ng.size() * 4);
     L.mat0 = w.add(mat0.data(), mat0.size() * 4);
     L.mat1 = w.add(mat1.data(), mat1.size() * 4);
+    if (gen) L.mat2 = w.add(mat2.data(), mat2.size() * 4);
     L.lt_a = w.add(lt_a.data(), lt_a.size() * 4);
     L.lt_e1 = w.add(lt_e1.data(), lt_e1.size() * 4);
     L.lt_e2 = w.add(lt_e2.data(), lt_e2.size() * 4);
     L.lt_t = w.add(lt_t.data(), lt_t.size() * 4);
+    if (gen) L.lt_g = w.add(lt_g.data(), lt_g.size() * 4);
     if (use_light_bvh) {
         const std::vector<float> lnodes = octant_nodes(s->light_bvh);
         L.lnodes = w.add(lnodes.data(), lnodes.size() * 4);
     }
+    if (s->blob_host.size() > 0xffffffffull || (uint64_t)std::max(s->bvh.n_nodes, s->light_bvh.n_nodes) * RT_NODE_BYTES > 0x7fffffffull)
+        return fail(RT_ERR_LIMIT, "scene exceeds the 4 GiB device blob / 2 GiB node array addressed by 32-bit offsets");
     L.total_bytes = (uint32_t)s->blob_host.size();
     L.n_nodes = s->bvh.n_nodes; L.n_tris = n; L.n_mats = s->n_mats; L.n_lights = n_lights;
     L.n_lnodes = s->light_bvh.n_nodes; L.light_bvh = use_light_bvh ? 1 : 0;
     L.max_leaf = s->bvh.max_leaf;
     L.inv_n_lights = n_lights > 0 ? 1.0f / (float)n_lights : 0.0f;
+    L.general = gen ? 1 : 0; L.n_planes = n_planes; L.has_dielectric = has_dielectric ? 1 : 0;
 
     // entry 0 = RT_CUR_DONE, one marker per walk; the light-pdf walk runs on top of a ray's live stack (wavefront kernel)
     const int need = s->bvh.depth + 3 + (use_light_bvh ? s->light_bvh.depth + 2 : 0);
@@ -396,8 +486,10 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
         if (!s->L.packed_refs) return fail(RT_ERR_LIMIT, "kernel_variant: scene too large for the shared-memory placement");
         plan->use_smem = true;
     }
-    plan->variant = kern == 0 ? env_int("RT_KERNEL", 3) : kern;
+    plan->variant = kern == 0 ? (s->L.general ? 3 : env_int("RT_KERNEL", 3)) : kern;
     if (plan->variant < 1 || plan->variant > 3) return fail(RT_ERR_INVALID, "kernel_variant: unknown kernel");
+    if (s->L.general && plan->variant != 3) return fail(RT_ERR_INVALID, "kernel_variant: general-primitive scenes (boxes, ellipsoids, planes, object transforms) run on the phased wavefront kernel (3x) only");
+    if (h.ray_depth < 0) return fail(RT_ERR_INVALID, "ray_depth must be >= 0");
     if (plan->variant != 1 && (long long)h.ray_depth * std::min(a.max_attempts, 127) + 1 >= (1 << 14))
         return fail(RT_ERR_LIMIT, "ray_depth x max_attempts exceeds the 14-bit Philox call counter of the wavefront kernel (lower max_attempts, or kernel_variant 10)");
     if (plan->variant != 1 && h.ray_depth > 255) return fail(RT_ERR_LIMIT, "ray_depth above 255 (the wavefront kernel packs the remaining depth in 8 bits; kernel_variant 10 has no limit)");
@@ -409,12 +501,12 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
         // automatic placement: staging the scene must not cost occupancy (a mid-size blob can push the block past half of the
         // SM's shared memory: one block per SM instead of two) -- fall back to the global-memory path in that case
         int with_smem = 0, without = 0;
-        cudaError_t es = rtd::render_resident_lanes(plan->variant, plan->cfg, true, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
+        cudaError_t es = rtd::render_resident_lanes(plan->variant, plan->cfg, true, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
         if (es != cudaSuccess) { cudaGetLastError(); with_smem = 0; }
-        CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, false, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &without));
+        CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, false, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &without));
         if (with_smem < without) { plan->use_smem = false; a.blob = s->blob_dev; }
     }
-    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
+    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
     const int n_samp = s1 - s0;
     // measured (B200): work items ~32x the resident path slots keep the end-of-frame tail short (512x512x1024 spp: +16 % over
     // 4x); frames with plenty of pixels still get up to 4 chunks of >= 128 samples (3840x2160x1024: +0.7 %)
@@ -494,6 +586,75 @@ int rt_scene_load_gltf(const char* path, int32_t width, int32_t height, int32_t 
     return finish_create(s, out);
 }
 
+int rt_scene_load_text(const char* path, int32_t width, int32_t height, int32_t samples, int32_t device, RtScene** out) {
+    if (!path || !out) return fail(RT_ERR_INVALID, "null argument");
+    *out = nullptr;
+    RtScene* s = new RtScene();
+    s->device = device;
+    rtb::LoadError err;
+    if (!rtb::load_text_scene(path, width, height, samples, &s->host, &err)) { delete s; return fail(err.code, err.message); }
+    return finish_create(s, out);
+}
+
+int rt_scene_load(const char* path, int32_t width, int32_t height, int32_t samples, int32_t device, RtScene** out) {
+    if (!path || !out) return fail(RT_ERR_INVALID, "null argument");
+    const size_t len = std::strlen(path);
+    if (len >= 4 && std::strcmp(path + len - 4, ".txt") == 0) return rt_scene_load_text(path, width, height, samples, device, out);
+    return rt_scene_load_gltf(path, width, height, samples, device, out);
+}
+
+int rt_scene_create2(const RtSceneDesc2* d2, int32_t device, RtScene** out) {
+    if (!d2 || !out) return fail(RT_ERR_INVALID, "null argument");
+    const bool ext = d2->shape_kind || d2->position || d2->rotation || d2->ior || d2->material_kind;
+    if (!ext) return rt_scene_create(&d2->base, device, out);
+    const RtSceneDesc* d = &d2->base;
+    *out = nullptr;
+    if (d->n_tris < 0) return fail(RT_ERR_INVALID, "n_tris < 0");
+    if (d->n_tris > 0 && (!d->tri_v || !d->tri_n || !d->tri_material || !d->tri_emission)) return fail(RT_ERR_INVALID, "null primitive array");
+    const size_t n = (size_t)d->n_tris;
+    for (size_t i = 0; i < n; ++i) {
+        if (d2->shape_kind && (d2->shape_kind[i] < RT_SHAPE_TRIANGLE || d2->shape_kind[i] > RT_SHAPE_PLANE)) return fail(RT_ERR_INVALID, "shape_kind out of range");
+        if (d2->material_kind && (d2->material_kind[i] < RT_MATERIAL_PBR || d2->material_kind[i] > RT_MATERIAL_DIELECTRIC)) return fail(RT_ERR_INVALID, "material_kind out of range");
+        if (d2->rotation) {
+            const double* q = d2->rotation + 4 * i;
+            const double n2 = q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3];
+            if (!(std::fabs(n2 - 1.0) <= 1e-6)) return fail(RT_ERR_INVALID, "rotation must be a unit quaternion (i, j, k, w)");
+        }
+        if (d2->ior && d2->material_kind && d2->material_kind[i] == RT_MATERIAL_DIELECTRIC && !(d2->ior[i] > 0.0)) return fail(RT_ERR_INVALID, "ior must be positive");
+    }
+    RtScene* s = nullptr;
+    RtScene* tmp = nullptr;
+    {   // the base fields go through the same copy as rt_scene_create (host-only), then the extension arrays are attached
+        const int rc = rt_scene_create(d, -1, &tmp);
+        if (rc != RT_OK) return rc;
+        s = new RtScene();
+        s->host = tmp->host;
+        rt_scene_destroy(tmp);
+    }
+    s->device = device;
+    rtb::HostScene& h = s->host;
+    h.kind.assign(n, RT_SHAPE_TRIANGLE); h.position.assign(n * 3, 0.0); h.rotation.assign(n * 4, 0.0); h.ior.assign(n, 1.0); h.mat_kind.assign(n, RT_MATERIAL_PBR);
+    for (size_t i = 0; i < n; ++i) h.rotation[i * 4 + 3] = 1.0;
+    if (d2->shape_kind) h.kind.assign(d2->shape_kind, d2->shape_kind + n);
+    if (d2->position) h.position.assign(d2->position, d2->position + n * 3);
+    if (d2->rotation) h.rotation.assign(d2->rotation, d2->rotation + n * 4);
+    if (d2->ior) h.ior.assign(d2->ior, d2->ior + n);
+    if (d2->material_kind) h.mat_kind.assign(d2->material_kind, d2->material_kind + n);
+    return finish_create(s, out);
+}
+
+int rt_scene_get_desc2(const RtScene* s, RtSceneDesc2* d) {
+    if (!s || !d) return fail(RT_ERR_INVALID, "null argument");
+    std::memset(d, 0, sizeof(*d));
+    const int rc = rt_scene_get_desc(s, &d->base);
+    if (rc != RT_OK) return rc;
+    const rtb::HostScene& h = s->host;
+    if (h.general()) {
+        d->shape_kind = h.kind.data(); d->position = h.position.data(); d->rotation = h.rotation.data(); d->ior = h.ior.data(); d->material_kind = h.mat_kind.data();
+    }
+    return RT_OK;
+}
+
 int rt_scene_create(const RtSceneDesc* d, int32_t device, RtScene** out) {
     if (!d || !out) return fail(RT_ERR_INVALID, "null argument");
     *out = nullptr;
@@ -542,7 +703,8 @@ int rt_scene_get_desc(const RtScene* s, RtSceneDesc* d) {
 int rt_scene_info(const RtScene* s, RtSceneInfo* o) {
     if (!s || !o) return fail(RT_ERR_INVALID, "null argument");
     std::memset(o, 0, sizeof(*o));
-    o->n_tris = s->host.n_tris(); o->n_lights = (int32_t)s->light_ids.size(); o->n_materials = s->n_mats;
+    o->n_tris = s->L.n_tris; o->n_lights = (int32_t)s->light_ids.size(); o->n_materials = s->n_mats;
+    o->n_infinite = s->L.n_planes; o->general_primitives = s->L.general;
     o->n_nodes = s->bvh.n_nodes; o->n_leaves = s->bvh.n_leaves; o->bvh_depth = s->bvh.depth; o->max_leaf_size = s->bvh.max_leaf;
     o->bvh_validate_failures = s->validate_failures; o->scene_in_shared_memory = s->use_smem ? 1 : 0; o->device = s->device;
     o->device_bytes = (int64_t)s->blob_host.size();
@@ -552,6 +714,8 @@ int rt_scene_info(const RtScene* s, RtSceneInfo* o) {
 
 int rt_scene_set_frame(RtScene* s, int32_t width, int32_t height, int32_t samples) {
     if (!s) return fail(RT_ERR_INVALID, "null scene");
+    if (width <= 0 || height <= 0 || samples < 0) return fail(RT_ERR_INVALID, "rt_scene_set_frame: width and height must be positive, samples >= 0");
+    if (width > 65535 || height > 65535) return fail(RT_ERR_LIMIT, "frame dimensions above 65535 (pixel coordinates are packed in 16 bits)");
     s->host.width = width; s->host.height = height; s->host.samples = samples;
     return RT_OK;
 }
@@ -844,29 +1008,45 @@ int rt_resolve_device(const float* accum_dev, int32_t width, int32_t height, uin
     return RT_OK;
 }
 
+namespace {
+int trace_rays_impl(RtScene* s, const double* rays, int64_t n, int32_t precision, int32_t* tri_id, double* t, double* hits);
+}
+int rt_trace_hits(RtScene* s, const double* rays, int64_t n, double* out) {
+    if (!s || !rays || !out || n < 0) return fail(RT_ERR_INVALID, "bad argument");
+    return trace_rays_impl(s, rays, n, 32, nullptr, nullptr, out);
+}
 int rt_trace_primary(RtScene* s, const double* rays, int64_t n, int32_t precision, int32_t* tri_id, double* t) {
     if (!s || !rays || !tri_id || !t || n < 0) return fail(RT_ERR_INVALID, "bad argument");
     if (precision != 32 && precision != 64) return fail(RT_ERR_INVALID, "precision must be 32 or 64");
+    return trace_rays_impl(s, rays, n, precision, tri_id, t, nullptr);
+}
+namespace {
+int trace_rays_impl(RtScene* s, const double* rays, int64_t n, int32_t precision, int32_t* tri_id, double* t, double* hits) {
     if (n == 0) return RT_OK;
     if (!s->blob_dev) return fail(RT_ERR_CUDA, "scene is host-only: no CUDA device bound, there is no CPU fallback");
+    if (precision == 64 && s->L.general) return fail(RT_ERR_INVALID, "precision 64 exists for triangle scenes only (f64 triangle test); general-primitive scenes trace in FP32");
     CUDA_TRY(cudaSetDevice(s->device));
     if (precision == 64 && !s->tri_d_dev) {
         CUDA_TRY(cudaMalloc((void**)&s->tri_d_dev, s->tri_d_host.size() * sizeof(double)));
         CUDA_TRY(cudaMemcpy(s->tri_d_dev, s->tri_d_host.data(), s->tri_d_host.size() * sizeof(double), cudaMemcpyHostToDevice));
     }
-    double *rays_d = nullptr, *t_d = nullptr; int32_t* id_d = nullptr;
+    double *rays_d = nullptr, *t_d = nullptr, *hits_d = nullptr; int32_t* id_d = nullptr;
     CUDA_TRY(cudaMalloc((void**)&rays_d, (size_t)n * 6 * sizeof(double)));
-    cudaError_t e = cudaMalloc((void**)&t_d, (size_t)n * sizeof(double));
-    if (e == cudaSuccess) e = cudaMalloc((void**)&id_d, (size_t)n * sizeof(int32_t));
+    cudaError_t e = cudaSuccess;
+    if (t) e = cudaMalloc((void**)&t_d, (size_t)n * sizeof(double));
+    if (e == cudaSuccess && tri_id) e = cudaMalloc((void**)&id_d, (size_t)n * sizeof(int32_t));
+    if (e == cudaSuccess && hits) e = cudaMalloc((void**)&hits_d, (size_t)n * 9 * sizeof(double));
     if (e == cudaSuccess) e = cudaMemcpyAsync(rays_d, rays, (size_t)n * 6 * sizeof(double), cudaMemcpyHostToDevice, s->stream);
-    if (e == cudaSuccess) e = rtd::launch_trace_rays(s->blob_dev, s->L, s->tri_d_dev, s->stack_entries, rays_d, n, precision == 64, id_d, t_d, s->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(tri_id, id_d, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream);
-    if (e == cudaSuccess) e = cudaMemcpyAsync(t, t_d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess) e = rtd::launch_trace_rays(s->blob_dev, s->L, s->tri_d_dev, s->stack_entries, rays_d, n, precision == 64, id_d, t_d, hits_d, s->stream);
+    if (e == cudaSuccess && tri_id) e = cudaMemcpyAsync(tri_id, id_d, (size_t)n * sizeof(int32_t), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && t) e = cudaMemcpyAsync(t, t_d, (size_t)n * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
+    if (e == cudaSuccess && hits) e = cudaMemcpyAsync(hits, hits_d, (size_t)n * 9 * sizeof(double), cudaMemcpyDeviceToHost, s->stream);
     if (e == cudaSuccess) e = cudaStreamSynchronize(s->stream);
-    cudaFree(rays_d); cudaFree(t_d); cudaFree(id_d);
+    cudaFree(rays_d); cudaFree(t_d); cudaFree(id_d); cudaFree(hits_d);
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("rt_trace_primary: ") + cudaGetErrorString(e));
     return RT_OK;
 }
+}  // namespace
 
 int rt_primary_rays(RtScene* s, const int32_t* xy, const double* xi, int64_t n, double* rays_out) {
     if (!s || !xy || !xi || !rays_out || n < 0) return fail(RT_ERR_INVALID, "bad argument");

@@ -69,6 +69,13 @@ struct SceneLayout {
     int32_t max_leaf;                            // largest leaf of the finite-primitive BVH (the kernel unrolls leaves of <= 2 triangles)
     float inv_n_lights;                          // 1 / n_lights (MultipleLightSamplingDistribution::pdf, distributions.rs:183)
     int32_t packed_refs;                         // 1: the x planes of `nodes` carry 16-bit child references (pair_step PACKED)
+    // ---- general-primitive scenes (Shape3D::Box + Object3D transforms, geometry.rs:27-46; text-scene shapes): `general` = 1
+    int32_t general;                             // 1: leaves index `prims` (RT_PRIM_BYTES records) instead of `tri_t`
+    uint32_t prims;                              // n_tris finite records in BVH order, then n_planes infinite ones (scene.rs:37)
+    uint32_t lt_g;                               // light records (same format, light order) for sampling and the pdf
+    uint32_t mat2;                               // per material: ior, material kind (as int bits), 0, 0
+    int32_t n_planes;
+    int32_t has_dielectric;                      // any material of kind RT_MAT_DIELECTRIC
 };
 #define RT_BRUTE_LIGHTS 8
 
@@ -260,6 +267,147 @@ RT_DEV void trace_nearest(const Space& sp, const SceneLayout& L, SmemStack& st, 
     }
 }
 
+// ------------------------------------------------------------------------------------------------ general primitives
+// Scenes that hold more than world-space triangles (Shape3D::Box, Object3D position / rotation: geometry.rs:27-46,196-251;
+// the text-scene shapes ELLIPSOID and PLANE: own spec) keep ONE 64-byte record per primitive:
+//   triangle : r0 = N | kind,  r1 = a | 1/area,  r2 = Au,  r3 = Av          (world space: the object transform is applied on the
+//              host -- the reference rotates the ray instead, geometry.rs:201-214; same hit, same t)
+//   others   : r0.xyz, r1.xyz, r2.xyz = rows of R^T (world -> object rotation = the conjugate quaternion of geometry.rs:206-213),
+//              r3.xyz = position, (r1.w, r2.w, r3.w) = s: box half sizes | ellipsoid radii | plane normal;  r0.w = kind
+#define RT_PRIM_BYTES 64u
+enum { RT_KIND_TRIANGLE = 0, RT_KIND_BOX = 1, RT_KIND_ELLIPSOID = 2, RT_KIND_PLANE = 3 };
+enum { RT_MAT_PBR = 0, RT_MAT_DIELECTRIC = 1 };
+#define RT_AUX_EXIT 4 /* aux bit: the hit leaves the solid (is_outer_to_inner == false, geometry.rs:180-188) */
+struct PrimRec { float4 r0, r1, r2, r3; };
+template <class Space>
+RT_DEV PrimRec load_prim(const Space& sp, uint32_t table, int i) {
+    const uint32_t o = table + (uint32_t)i * RT_PRIM_BYTES;
+    PrimRec R; R.r0 = sp.ld4(o); R.r1 = sp.ld4(o + 16u); R.r2 = sp.ld4(o + 32u); R.r3 = sp.ld4(o + 48u);
+    return R;
+}
+RT_DEV int prim_kind(const PrimRec& R) { return __float_as_int(R.r0.w); }
+RT_DEV float3 prim_s(const PrimRec& R) { return f3(R.r1.w, R.r2.w, R.r3.w); }
+RT_DEV float3 prim_to_local(const PrimRec& R, float3 v) { return f3(dot(f3(R.r0), v), dot(f3(R.r1), v), dot(f3(R.r2), v)); }   // q.conjugate() * v
+RT_DEV float3 prim_to_world(const PrimRec& R, float3 v) { return f3(R.r0) * v.x + f3(R.r1) * v.y + f3(R.r2) * v.z; }          // q * v
+
+// FIRST hit of a primitive = what competes in the nearest-hit query (points.0[0], bvh.rs:269) and what
+// intersect_ray_with_object3d returns (geometry.rs:51-58,196-223).  Out: t; triangles: (u, v) barycentrics; others: u = t,
+// v = aux bits (box: axis 0..2 of the face; RT_AUX_EXIT when the ray leaves the solid / hits the back of a plane).
+//   box       geometry.rs:140-194: object-space slabs, entry hit if t_min > 0, else the exit hit if t_max > 0.  The face is the
+//             slab that produced the hit (x, y, z priority on ties, like the `s - |p| < EPS` cascade of :161-169 at edges).
+//   ellipsoid own spec: |(o + t d)/r|^2 = 1 around the closest approach (no cancellation in FP32); outside -> entry root if the
+//             ray approaches, inside -> exit root.  Same roots as the oracle's half-b form.
+//   plane     own spec: t = n.(pos - o) / n.d with the world normal n = R s.
+RT_DEV bool prim_first_hit(const PrimRec& R, float3 o, float3 d, float& t, float& u, float& v) {
+    const int kind = prim_kind(R);
+    if (kind == RT_KIND_TRIANGLE) {
+        TriTest T; T.N = f3(R.r0); T.a = f3(R.r1); T.Au = f3(R.r2); T.Av = f3(R.r3);
+        return tri_test(o, d, T, t, u, v);
+    }
+    const float3 s = prim_s(R);
+    const float3 rel = o - f3(R.r3);
+    if (kind == RT_KIND_PLANE) {
+        const float3 nw = prim_to_world(R, s);
+        const float dn = dot(nw, d);
+        t = -dot(nw, rel) * fast_rcp(dn);
+        u = t; v = __int_as_float(dn < 0.0f ? 0 : RT_AUX_EXIT);
+        return t > 0.0f;                                   // dn == 0: +-inf / NaN, rejected here or by the caller's `t < best`
+    }
+    const float3 ol = prim_to_local(R, rel), dl = prim_to_local(R, d);
+    if (kind == RT_KIND_BOX) {
+        const float3 inv = safe_inv_dir(dl);
+        const float ax = (-s.x - ol.x) * inv.x, bx = (s.x - ol.x) * inv.x;
+        const float ay = (-s.y - ol.y) * inv.y, by = (s.y - ol.y) * inv.y;
+        const float az = (-s.z - ol.z) * inv.z, bz = (s.z - ol.z) * inv.z;
+        const float nx = fminf(ax, bx), fx = fmaxf(ax, bx), ny = fminf(ay, by), fy = fmaxf(ay, by), nz = fminf(az, bz), fz = fmaxf(az, bz);
+        const float tmin = max3f(nx, ny, nz), tmax = min3f(fx, fy, fz);
+        if (!(tmin <= tmax)) return false;
+        const bool entry = tmin > 0.0f;
+        t = entry ? tmin : tmax;
+        const int axis = entry ? ((nx >= ny && nx >= nz) ? 0 : (ny >= nz ? 1 : 2)) : ((fx <= fy && fx <= fz) ? 0 : (fy <= fz ? 1 : 2));
+        u = t; v = __int_as_float(axis | (entry ? 0 : RT_AUX_EXIT));
+        return t > 0.0f;
+    }
+    // ellipsoid
+    const float3 ir = f3(fast_rcp(s.x), fast_rcp(s.y), fast_rcp(s.z));
+    const float3 od = ol * ir, dd = dl * ir;
+    const float a = dot(dd, dd), hb = dot(od, dd), c = dot(od, od) - 1.0f;
+    const float ia = fast_rcp(a);
+    const float tc = -hb * ia;
+    const float3 pc = fma3(dd, tc, od);                    // closest approach to the centre, unit-sphere space
+    const float h2 = (1.0f - dot(pc, pc)) * ia;
+    if (!(h2 >= 0.0f)) return false;
+    const float h = fast_sqrt(h2);
+    const bool inside = c < 0.0f;
+    t = inside ? tc + h : tc - h;
+    u = t; v = __int_as_float(inside ? RT_AUX_EXIT : 0);
+    return inside ? t > 0.0f : (hb < 0.0f && t > 0.0f);
+}
+
+// intersect_ray_with_scene (rendering.rs:201-226) for general-primitive scenes: the nearest-hit walk of trace_nearest with
+// prim_first_hit at the leaves, then the linear scan of the infinite primitives (records n_tris .. n_tris + n_planes) under
+// the running bound with strict `<` (:215-224).  hit.tri indexes `prims`; (hit.u, hit.v) = barycentrics or (t, aux).
+// skip_prim: see trace_nearest -- set by the caller only when a re-hit is impossible in exact arithmetic.
+template <class Space, bool STATS>
+RT_DEV void trace_nearest_gen(const Space& sp, const SceneLayout& L, SmemStack& st, float3 o, float3 d, int skip_prim, Hit& hit, Counters& cnt) {
+    const RaySetup r = ray_setup(o, d, L.nodes);
+    hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
+    st.push(RT_CUR_DONE);
+    int cur = 0;
+    for (;;) {
+        while (cur >= 0) {
+            pair_step(sp, L.nodes, r, hit.t, cur, st);
+            if (STATS) cnt.node_tests += 2;
+        }
+        if (cur == RT_CUR_DONE) break;
+        const uint32_t code = (uint32_t)~cur;
+        const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
+        for (int i = first; i < first + n; ++i) {
+            float t, u, v;
+            const bool ok = prim_first_hit(load_prim(sp, L.prims, i), o, d, t, u, v);
+            if (STATS) cnt.tri_tests += 1;
+            if (ok && t < hit.t && i != skip_prim) { hit.t = t; hit.u = u; hit.v = v; hit.tri = i; }
+        }
+        cur = st.pop();
+    }
+    for (int i = L.n_tris; i < L.n_tris + L.n_planes; ++i) {
+        float t, u, v;
+        const bool ok = prim_first_hit(load_prim(sp, L.prims, i), o, d, t, u, v);
+        if (STATS) cnt.tri_tests += 1;
+        if (ok && t < hit.t && i != skip_prim) { hit.t = t; hit.u = u; hit.v = v; hit.tri = i; }
+    }
+}
+
+// What get_ray_color (rendering.rs:96-101,107) reads from the hit of a non-triangle primitive: normal_geometry in WORLD space
+// (rotated back, geometry.rs:245-249), normal_shading LEFT IN OBJECT SPACE (the reference does not rotate it back; it only
+// gates acceptance, rendering.rs:107), both facing the incoming ray; `outer` = is_outer_to_inner.
+struct HitFrame { float3 n, ns; bool outer; };
+RT_DEV HitFrame prim_frame(const PrimRec& R, float3 o, float3 d, float t, int aux) {
+    const int kind = prim_kind(R);
+    HitFrame F;
+    F.outer = !(aux & RT_AUX_EXIT);
+    float3 nl;
+    if (kind == RT_KIND_PLANE) {
+        nl = prim_s(R);
+        if (!F.outer) nl = -nl;
+    } else if (kind == RT_KIND_BOX) {
+        const float3 dl = prim_to_local(R, d);
+        const int axis = aux & 3;
+        const float da = axis == 0 ? dl.x : (axis == 1 ? dl.y : dl.z);
+        const float sg = da > 0.0f ? -1.0f : 1.0f;        // entry: the face whose outward normal opposes d; exit: -(outward normal)
+        nl = f3(axis == 0 ? sg : 0.0f, axis == 1 ? sg : 0.0f, axis == 2 ? sg : 0.0f);
+    } else {
+        const float3 s = prim_s(R);
+        const float3 pl = prim_to_local(R, fma3(d, t, o - f3(R.r3)));
+        const float3 ir2 = f3(fast_rcp(s.x * s.x), fast_rcp(s.y * s.y), fast_rcp(s.z * s.z));
+        nl = normalize(pl * ir2);
+        if (!F.outer) nl = -nl;
+    }
+    F.ns = nl;
+    F.n = prim_to_world(R, nl);
+    return F;
+}
+
 // ------------------------------------------------------------------------------------------------ BRDF pieces
 // GGX terms shared by specular_brdf (rendering.rs:157-184) and the VNDF pdf (distributions.rs:236-260,
 // 276-297).  In the local frame of distributions.rs the half vector has x^2+y^2 = 1-(n.h)^2, so Dn(:245-252)
@@ -355,16 +503,103 @@ RT_DEV float light_tri_pdf(const Space& sp, const SceneLayout& L, int i, float3 
     return r0.w * t * t * fast_rcp(fabsf(dot(T.N, l)));   // l is unit: |p - point|^2 = t^2, omega = l, N = unit normal
 }
 
-// MultipleLightSamplingDistribution::pdf (distributions.rs:160-184): sum over ALL light triangles the ray
+// ---- lights that are general primitives (Shape3D::Box arm of distributions.rs:70-148; ellipsoid: own spec) ----------------
+// DirectLightSamplingDistribution::sample_unit_vector (distributions.rs:84-125) for light `idx` (chosen uniformly by count,
+// :151-158).  Box arm :86-110: a face pair picked by area from x in [0, wx+wy+wz), a random sign, two uniform in-face
+// coordinates.  `bits` supplies x (bits 0..30) and the sign (bit 31); the reference spends separate draws (gen_range,
+// gen_bool) -- the streams differ anyway.  Ellipsoid (own spec): radii (.) a uniform point of the unit sphere.
+template <class Space>
+RT_DEV float3 sample_light_gen(const Space& sp, const SceneLayout& L, float3 point, int idx, float u1, float u2, uint32_t bits) {
+    const PrimRec R = load_prim(sp, L.lt_g, idx);
+    const int kind = prim_kind(R);
+    if (kind == RT_KIND_TRIANGLE) return sample_light(sp, L, point, idx, u1, u2);
+    const float3 s = prim_s(R);
+    float3 pl;
+    if (kind == RT_KIND_BOX) {
+        const float wx = s.y * s.z, wy = s.x * s.z, wz = s.x * s.y;                  // the common factor 4 of :87 cancels
+        const float x = u01(bits << 1) * (wx + wy + wz);
+        const float sg = (bits >> 31) ? 1.0f : -1.0f;
+        const float c1 = fmaf(2.0f, u1, -1.0f), c2 = fmaf(2.0f, u2, -1.0f);         // gen_range(-s..s) = (2u - 1) s
+        if (x < wx) pl = f3(s.x * sg, c1 * s.y, c2 * s.z);
+        else if (x < wx + wy) pl = f3(c1 * s.x, s.y * sg, c2 * s.z);
+        else pl = f3(c1 * s.x, c2 * s.y, s.z * sg);
+    } else {
+        pl = sphere_uniform(u1, u2) * s;
+    }
+    return normalize(prim_to_world(R, pl) + f3(R.r3) - point);                       // :121-124
+}
+
+// One light's term of MultipleLightSamplingDistribution::pdf (distributions.rs:166-182) for a general primitive: EVERY hit of
+// the ray with the light (entry and exit of a box: intersect_ray_with_object3d_all_points, geometry.rs:226-251) adds
+// local_pdf * |p - point|^2 / |ng . omega|; l is unit, so |p - point|^2 = t^2 and, R being orthonormal, ng . omega is
+// evaluated in object space.  local_pdf: get_local_pdf (:70-81): box 1 / (8 (sx sy + sy sz + sz sx)); ellipsoid (own spec)
+// 1 / (4 pi sqrt((ux ry rz)^2 + (rx uy rz)^2 + (rx ry uz)^2)) at the unit-sphere point u = p / r.
+template <class Space>
+RT_DEV float light_prim_pdf(const Space& sp, const SceneLayout& L, int i, float3 point, float3 l) {
+    const PrimRec R = load_prim(sp, L.lt_g, i);
+    const int kind = prim_kind(R);
+    if (kind == RT_KIND_TRIANGLE) {
+        TriTest T; T.N = f3(R.r0); T.a = f3(R.r1); T.Au = f3(R.r2); T.Av = f3(R.r3);
+        float t, u, v;
+        if (!tri_test(point, l, T, t, u, v)) return 0.0f;
+        return R.r1.w * t * t * fast_rcp(fabsf(dot(T.N, l)));
+    }
+    const float3 s = prim_s(R);
+    const float3 ol = prim_to_local(R, point - f3(R.r3)), dl = prim_to_local(R, l);
+    if (kind == RT_KIND_BOX) {
+        const float3 inv = safe_inv_dir(dl);
+        const float ax = (-s.x - ol.x) * inv.x, bx = (s.x - ol.x) * inv.x;
+        const float ay = (-s.y - ol.y) * inv.y, by = (s.y - ol.y) * inv.y;
+        const float az = (-s.z - ol.z) * inv.z, bz = (s.z - ol.z) * inv.z;
+        const float nx = fminf(ax, bx), fx = fmaxf(ax, bx), ny = fminf(ay, by), fy = fmaxf(ay, by), nz = fminf(az, bz), fz = fmaxf(az, bz);
+        const float tmin = max3f(nx, ny, nz), tmax = min3f(fx, fy, fz);
+        if (!(tmin <= tmax) || !(tmax > 0.0f)) return 0.0f;
+        const float local_pdf = fast_rcp(8.0f * (s.x * s.y + s.y * s.z + s.z * s.x));
+        const float dn = fabsf((nx >= ny && nx >= nz) ? dl.x : (ny >= nz ? dl.y : dl.z));
+        const float df = fabsf((fx <= fy && fx <= fz) ? dl.x : (fy <= fz ? dl.y : dl.z));
+        float sum = tmax * tmax * fast_rcp(df);
+        if (tmin > 0.0f) sum += tmin * tmin * fast_rcp(dn);
+        return local_pdf * sum;
+    }
+    if (kind != RT_KIND_ELLIPSOID) return 0.0f;                                       // planes are never lights
+    const float3 ir = f3(fast_rcp(s.x), fast_rcp(s.y), fast_rcp(s.z));
+    const float3 od = ol * ir, dd = dl * ir;
+    const float a = dot(dd, dd), hb = dot(od, dd), c = dot(od, od) - 1.0f;
+    const float ia = fast_rcp(a);
+    const float tc = -hb * ia;
+    const float3 pc = fma3(dd, tc, od);
+    const float h2 = (1.0f - dot(pc, pc)) * ia;
+    if (!(h2 >= 0.0f)) return 0.0f;
+    const float h = fast_sqrt(h2);
+    const bool inside = c < 0.0f;
+    if (!inside && !(hb < 0.0f)) return 0.0f;
+    const float3 rr = f3(s.y * s.z, s.x * s.z, s.x * s.y);
+    float sum = 0.0f;
+#pragma unroll
+    for (int k = 0; k < 2; ++k) {
+        const float t = k == 0 ? tc - h : tc + h;
+        if (k == 0 && inside) continue;
+        if (!(t > 0.0f)) continue;
+        const float3 us = fma3(dd, t, od);                                            // unit-sphere point
+        const float3 j = us * rr;
+        const float local_pdf = fast_rcp(4.0f * RT_PI_F) * fast_rsqrt(dot(j, j));
+        const float3 nl = normalize(us * ir);                                         // object-space normal p / r^2
+        sum += local_pdf * t * t * fast_rcp(fabsf(dot(nl, dl)));
+    }
+    return sum;
+}
+
+// MultipleLightSamplingDistribution::pdf (distributions.rs:160-184): sum over ALL lights the ray
 // pierces, divided by the light count.  Few lights: plain loop (the reference's light BVH is a single leaf for
 // every shipped scene).  Many lights: all-hits walk of the light BVH = intersect_with_bvh_all_points
-// (bvh.rs:174-229): no pruning by distance, every intersected leaf triangle contributes.  The walk pushes its own
+// (bvh.rs:174-229): no pruning by distance, every intersected leaf primitive contributes.  The walk pushes its own
 // RT_CUR_DONE marker first, so it can run on top of the traversal stack of a ray that is still in flight.
-template <class Space, bool STATS>
+// GEN: the lights are general primitives (light_prim_pdf) instead of triangle TEST records (light_tri_pdf).
+template <class Space, bool STATS, bool GEN = false>
 RT_DEV float light_pdf(const Space& sp, const SceneLayout& L, SmemStack& st, float3 point, float3 l, Counters& cnt) {
     float sum = 0.0f;
     if (!L.light_bvh) {
-        for (int i = 0; i < L.n_lights; ++i) sum += light_tri_pdf(sp, L, i, point, l);
+        for (int i = 0; i < L.n_lights; ++i) sum += GEN ? light_prim_pdf(sp, L, i, point, l) : light_tri_pdf(sp, L, i, point, l);
         if (STATS) cnt.light_tri_tests += (unsigned long long)L.n_lights;
     } else {
         const RaySetup r = ray_setup(point, l, L.lnodes);
@@ -375,7 +610,7 @@ RT_DEV float light_pdf(const Space& sp, const SceneLayout& L, SmemStack& st, flo
             if (cur == RT_CUR_DONE) break;
             const uint32_t code = (uint32_t)~cur;
             const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
-            for (int i = first; i < first + n; ++i) sum += light_tri_pdf(sp, L, i, point, l);
+            for (int i = first; i < first + n; ++i) sum += GEN ? light_prim_pdf(sp, L, i, point, l) : light_tri_pdf(sp, L, i, point, l);
             if (STATS) cnt.light_tri_tests += (unsigned long long)n;
             cur = st.pop();
         }

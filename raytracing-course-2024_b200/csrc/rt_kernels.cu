@@ -50,6 +50,59 @@ RT_DEV Material load_material(const Space& sp, const SceneLayout& L, int id) {
     return m;
 }
 
+// What get_ray_color (rendering.rs:96-101,107) takes from a hit: corrected_point = o + d (t - EPS) (:98), normal_geometry
+// (sampling, pdfs, BRDF, cosine) and normal_shading (acceptance gate only) both facing the incoming ray, is_outer_to_inner.
+// Triangles: the point comes from the barycentrics (on the triangle's plane to ~1 ulp), the shading normal is interpolated and
+// left un-normalised (only its sign test is used).  GEN scenes dispatch on the primitive record (prim_frame); `flat` says that a
+// ray leaving the primitive can never meet it again (triangles, planes), which the self-hit skip relies on.
+struct Vertex { float3 P, surf, n, ns; bool outer, flat; };
+template <class Space, bool GEN>
+RT_DEV Vertex hit_vertex(const Space& sp, const SceneLayout& L, int tri, float4 n0, float3 o, float3 din, float hu, float hv) {
+    Vertex V;
+    const uint32_t o16 = (uint32_t)tri * 16u;
+    if (GEN) {
+        const PrimRec R = load_prim(sp, L.prims, tri);
+        const int kind = prim_kind(R);
+        if (kind != RT_KIND_TRIANGLE) {
+            const HitFrame F = prim_frame(R, o, din, hu, __float_as_int(hv));
+            V.n = F.n; V.ns = F.ns; V.outer = F.outer; V.flat = kind == RT_KIND_PLANE;
+            V.surf = fma3(din, hu, o);
+            V.P = fma3(din, -RT_EPS_F, V.surf);
+            return V;
+        }
+    }
+    const float3 ng = f3(sp.ld4(L.sh_ng + o16));
+    V.outer = dot(ng, din) < 0.0f;
+    const float sgn = V.outer ? 1.0f : -1.0f;                    // geometry.rs:115-126
+    V.n = ng * sgn;
+    const float3 dn1 = f3(sp.ld4(L.sh_dn1 + o16)), dn2 = f3(sp.ld4(L.sh_dn2 + o16));
+    V.ns = (f3(n0) + dn1 * hu + dn2 * hv) * sgn;
+    const float3 ta = f3(sp.ld4(L.tri_a + o16)), te1 = f3(sp.ld4(L.tri_e1 + o16)), te2 = f3(sp.ld4(L.tri_e2 + o16));
+    V.surf = fma3(te2, hv, fma3(te1, hu, ta));
+    V.P = fma3(din, -RT_EPS_F, V.surf);                          // :98
+    V.flat = true;
+    return V;
+}
+
+// [OWN SPEC, DESIGN.md section 12 -- reference HEAD has no transmissive material, only the dead fields `ior` (scene.rs:18) and
+// `is_outer_to_inner` (geometry.rs:23)]  Smooth dielectric, delta BSDF: eta = n_from / n_to with the outside index 1, Schlick
+// reflectance, total internal reflection reflects, ONE uniform picks reflection (u < R) or refraction; the refracted ray
+// starts EPS BEHIND the surface and is tinted by the base colour when it ENTERS the solid.  Returns true for refraction.
+RT_DEV bool dielectric_sample(float3 n, float3 v, float nv, float ior, bool outer, float u, float3& l) {
+    const float eta = outer ? fast_rcp(ior) : ior;
+    const float sin2sq = eta * eta * fmaxf(0.0f, fmaf(-nv, nv, 1.0f));
+    bool refract = false;
+    float cos2 = 0.0f;
+    if (sin2sq < 1.0f) {
+        cos2 = fast_sqrt(1.0f - sin2sq);
+        const float q = (eta - 1.0f) * fast_rcp(eta + 1.0f), r0 = q * q;
+        const float refl = fmaf(1.0f - r0, pow5(1.0f - nv), r0);
+        refract = !(u < refl);
+    }
+    l = refract ? normalize(n * fmaf(eta, nv, -cos2) - v * eta) : normalize(n * (2.0f * nv) - v);   // geometry.rs:65-69 for the mirror arm
+    return refract;
+}
+
 // get_ray_to_pixel (rendering.rs:71-84) with explicit jitter.
 RT_DEV void camera_ray(const Camera& c, int W, int H, int x, int y, float xi1, float xi2, float3& o, float3& d) {
     const float rx = (float)x + xi1, ry = (float)y + xi2;
@@ -63,17 +116,18 @@ RT_DEV void camera_ray(const Camera& c, int W, int H, int x, int y, float xi1, f
 // One iteration of the rejection loop rendering.rs:102-110: MixDistribution::sample_unit_vector
 // (distributions.rs:188-192) followed by MixDistribution::pdf (:194-201).  Returns the mixture pdf; `terms` are
 // the per-direction quantities for the BRDF of the accepted direction.
-template <class Space, bool STATS>
+template <class Space, bool STATS, bool GEN = false>
 RT_DEV float mix_sample_and_pdf(const Space& sp, const SceneLayout& L, SmemStack& st, int n_comp, float inv_n_comp, float3 P, float3 n, float3 v,
                                 float nv, float alpha, float alpha2, float g1v, uint4 rnd, float3& l, DirTerms& terms, Counters& cnt) {
     const uint32_t comp = __umulhi(rnd.x, (uint32_t)n_comp);           // gen_range(0..len)
     const float u1 = u01(rnd.y), u2 = u01(rnd.z);
     if (comp == 0u) l = sample_cosine(n, u1, u2);
     else if (comp == 1u) l = sample_vndf(n, v, alpha, u1, u2);
-    else l = sample_light(sp, L, P, (int)__umulhi(rnd.w, (uint32_t)L.n_lights), u1, u2);
+    else if (!GEN) l = sample_light(sp, L, P, (int)__umulhi(rnd.w, (uint32_t)L.n_lights), u1, u2);
+    else l = sample_light_gen(sp, L, P, (int)__umulhi(rnd.w, (uint32_t)L.n_lights), u1, u2, rnd.w * (uint32_t)L.n_lights);   // low product word: uniform given the index
     terms = dir_terms(n, v, l, alpha2);
     float pdf = pdf_cosine(terms.nl) + pdf_vndf(terms.d_nochi, g1v, nv);
-    if (n_comp == 3) pdf += light_pdf<Space, STATS>(sp, L, st, P, l, cnt);
+    if (n_comp == 3) pdf += light_pdf<Space, STATS, GEN>(sp, L, st, P, l, cnt);
     return pdf * inv_n_comp;
 }
 
@@ -253,7 +307,8 @@ static cudaError_t launch_render_t(const RenderArgs& a, int device_sms, cudaStre
 #include "rt_render_wave.cuh"
 
 // variant: 1 = v1 per-lane megakernel, 2 = v3 warp-local wavefront with while-while bursts, 3 = v3 with phased bursts.
-// cfg (v3 only): resident-thread configuration, see wave_cfg_name().
+// cfg (v3 only): resident-thread configuration, see wave_cfg_name().  General-primitive scenes (a.L.general) run on the phased
+// wavefront kernel only, 256 threads x 2 blocks per SM (the wider vertex code wants more than the 80 registers of 384 x 2).
 static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int sms, cudaStream_t s, KernelInfo* info, bool launch, int* lanes) {
 #define RT_DISPATCH(FN, ...)                                                                                                   \
     (use_smem ? (stats ? FN<SmemSpace, true __VA_ARGS__>(a, sms, s, info, launch, lanes) : FN<SmemSpace, false __VA_ARGS__>(a, sms, s, info, launch, lanes)) \
@@ -266,6 +321,10 @@ static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bo
         case 4: return RT_DISPATCH(launch_wave_t, , MODE, 512, 2);        \
         default: return RT_DISPATCH(launch_wave_t, , MODE, 256, 2);       \
     }
+    if (a.L.general) {
+        if (variant != 3) return cudaErrorInvalidValue;
+        return RT_DISPATCH(launch_wave_t, , 1, 256, 2, true);
+    }
     if (variant == 1) return RT_DISPATCH(launch_render_t);
     if (variant == 3) { RT_WAVE(1) }
     RT_WAVE(0)
@@ -275,10 +334,10 @@ static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bo
 cudaError_t launch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info) {
     return dispatch_render(a, variant, cfg, use_smem, stats, device_sms, stream, info, true, nullptr);
 }
-cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes) {
+cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, bool general, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes) {
     RenderArgs a;
     memset(&a, 0, sizeof(a));
-    a.L.total_bytes = blob_bytes; a.stack_entries = stack_entries;
+    a.L.total_bytes = blob_bytes; a.stack_entries = stack_entries; a.L.general = general ? 1 : 0;
     return dispatch_render(a, variant, cfg, use_smem, stats, device_sms, 0, nullptr, false, lanes);
 }
 
@@ -350,9 +409,12 @@ __device__ __forceinline__ bool tri_test_f64(const double* o, const double* d, c
     return u >= 0.0 && v >= 0.0 && u + v <= 1.0 && t > 0.0;
 }
 
-template <bool F64>
+// hits (optional, 9 doubles per ray): t, normal_geometry, normal_shading (normalised here for comparison), original id,
+// is_outer_to_inner -- the vertex frame exactly as the render kernel builds it (hit_vertex).
+template <bool F64, bool GEN>
 __global__ void __launch_bounds__(128) trace_rays_kernel(const char* blob, const SceneLayout L, const double* __restrict__ tri_d, uint32_t stack_entries,
-                                                         const double* __restrict__ rays, long long n, int32_t* __restrict__ tri_id, double* __restrict__ t_out) {
+                                                         const double* __restrict__ rays, long long n, int32_t* __restrict__ tri_id, double* __restrict__ t_out,
+                                                         double* __restrict__ hits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
     SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u);
@@ -362,9 +424,11 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const char* blob, const
     double od[3] = {rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]}, dd[3] = {rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]};
     const float3 o = f3((float)od[0], (float)od[1], (float)od[2]), d = f3((float)dd[0], (float)dd[1], (float)dd[2]);
     int best = -1; double best_t = 1.0 / 0.0;
+    Hit hit; hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
     if (!F64) {
-        Hit hit; Counters cnt; cnt.node_tests = 0; cnt.tri_tests = 0; cnt.light_tri_tests = 0;
-        trace_nearest<GmemSpace, false>(sp, L, st, o, d, -1, hit, cnt);
+        Counters cnt; cnt.node_tests = 0; cnt.tri_tests = 0; cnt.light_tri_tests = 0;
+        if (GEN) trace_nearest_gen<GmemSpace, false>(sp, L, st, o, d, -1, hit, cnt);
+        else trace_nearest<GmemSpace, false>(sp, L, st, o, d, -1, hit, cnt);
         best = hit.tri; best_t = hit.tri >= 0 ? (double)hit.t : best_t;
     } else {
         const RaySetup r = ray_setup(o, d, L.nodes);
@@ -385,26 +449,33 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const char* blob, const
             cur = st.pop();
         }
     }
-    tri_id[i] = best >= 0 ? __float_as_int(sp.ld4(L.sh_dn1 + (uint32_t)best * 16u).w) : -1;
-    t_out[i] = best_t;
+    const int orig = best >= 0 ? __float_as_int(sp.ld4(L.sh_dn1 + (uint32_t)best * 16u).w) : -1;
+    if (tri_id) tri_id[i] = orig;
+    if (t_out) t_out[i] = best_t;
+    if (hits && !F64) {
+        double* h = hits + 9 * i;
+        if (best < 0) { h[0] = best_t; for (int k = 1; k < 7; ++k) h[k] = 0.0; h[7] = -1.0; h[8] = 0.0; return; }
+        const Vertex V = hit_vertex<GmemSpace, GEN>(sp, L, best, sp.ld4(L.sh_n0 + (uint32_t)best * 16u), o, d, hit.u, hit.v);
+        const float3 ns = normalize(V.ns);
+        h[0] = best_t; h[1] = V.n.x; h[2] = V.n.y; h[3] = V.n.z; h[4] = ns.x; h[5] = ns.y; h[6] = ns.z; h[7] = (double)orig; h[8] = V.outer ? 1.0 : 0.0;
+    }
 }
 cudaError_t launch_trace_rays(const char* blob, const SceneLayout& L, const double* tri_d, uint32_t stack_entries, const double* rays, long long n,
-                              bool f64, int32_t* tri_id, double* t, cudaStream_t stream) {
+                              bool f64, int32_t* tri_id, double* t, double* hits, cudaStream_t stream) {
     if (n <= 0) return cudaSuccess;
+    if (L.general && f64) return cudaErrorInvalidValue;          // f64 primitive tests exist for triangles only
     const int block = 128;
     const uint32_t smem = stack_entries * block * 4u;
     const int grid = (int)((n + block - 1) / block);
-    cudaError_t e;
-    if (f64) {
-        e = cudaFuncSetAttribute(trace_rays_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    auto go = [&](auto kern) {
+        cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        trace_rays_kernel<true><<<grid, block, smem, stream>>>(blob, L, tri_d, stack_entries, rays, n, tri_id, t);
-    } else {
-        e = cudaFuncSetAttribute(trace_rays_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        trace_rays_kernel<false><<<grid, block, smem, stream>>>(blob, L, tri_d, stack_entries, rays, n, tri_id, t);
-    }
-    return cudaGetLastError();
+        kern<<<grid, block, smem, stream>>>(blob, L, tri_d, stack_entries, rays, n, tri_id, t, hits);
+        return cudaGetLastError();
+    };
+    if (f64) return go(trace_rays_kernel<true, false>);
+    if (L.general) return go(trace_rays_kernel<false, true>);
+    return go(trace_rays_kernel<false, false>);
 }
 
 __global__ void primary_rays_kernel(const Camera cam, int W, int H, const int32_t* __restrict__ xy, const double* __restrict__ xi, long long n, double* __restrict__ rays) {
@@ -426,13 +497,13 @@ int eval_in_width(int fn) {
     switch (fn) {
         case RT_FN_BRDF: return 14; case RT_FN_PDF_COSINE: return 6; case RT_FN_PDF_VNDF: return 10; case RT_FN_PDF_LIGHT: return 6;
         case RT_FN_PDF_MIX: return 13; case RT_FN_SAMPLE_COSINE: return 5; case RT_FN_SAMPLE_VNDF: return 9; case RT_FN_SAMPLE_LIGHT: return 6;
-        case RT_FN_PHILOX: return 4; default: return 0;
+        case RT_FN_PHILOX: return 4; case RT_FN_SAMPLE_LIGHT_GEN: return 8; case RT_FN_DIELECTRIC: return 9; default: return 0;
     }
 }
 int eval_out_width(int fn) {
     switch (fn) {
         case RT_FN_BRDF: return 3; case RT_FN_PDF_COSINE: case RT_FN_PDF_VNDF: case RT_FN_PDF_LIGHT: case RT_FN_PDF_MIX: return 1;
-        case RT_FN_SAMPLE_COSINE: return 6; case RT_FN_SAMPLE_VNDF: case RT_FN_SAMPLE_LIGHT: return 3; case RT_FN_PHILOX: return 4; default: return 0;
+        case RT_FN_SAMPLE_COSINE: return 6; case RT_FN_SAMPLE_VNDF: case RT_FN_SAMPLE_LIGHT: case RT_FN_SAMPLE_LIGHT_GEN: return 3; case RT_FN_PHILOX: case RT_FN_DIELECTRIC: return 4; default: return 0;
     }
 }
 
@@ -465,7 +536,8 @@ __global__ void __launch_bounds__(128) eval_kernel(const char* blob, const Scene
         const float nv = dot(nn, v);
         y[0] = pdf_vndf(t.d_nochi, ggx_g1(nv, alpha2), nv);
     } else if (fn == RT_FN_PDF_LIGHT) {
-        y[0] = L.n_lights > 0 ? light_pdf<GmemSpace, false>(sp, L, st, f3(x[0], x[1], x[2]), f3(x[3], x[4], x[5]), cnt) : 0.0f;
+        const float3 P = f3(x[0], x[1], x[2]), l = f3(x[3], x[4], x[5]);
+        y[0] = L.n_lights <= 0 ? 0.0f : (L.general ? light_pdf<GmemSpace, false, true>(sp, L, st, P, l, cnt) : light_pdf<GmemSpace, false>(sp, L, st, P, l, cnt));
     } else if (fn == RT_FN_PDF_MIX) {
         const float3 P = f3(x[0], x[1], x[2]), nn = f3(x[3], x[4], x[5]), l = f3(x[6], x[7], x[8]), v = f3(x[9], x[10], x[11]);
         const float alpha = x[12] * x[12], alpha2 = alpha * alpha;
@@ -473,7 +545,7 @@ __global__ void __launch_bounds__(128) eval_kernel(const char* blob, const Scene
         const float nv = dot(nn, v);
         float pdf = pdf_cosine(t.nl) + pdf_vndf(t.d_nochi, ggx_g1(nv, alpha2), nv);
         const int n_comp = L.n_lights > 0 ? 3 : 2;
-        if (n_comp == 3) pdf += light_pdf<GmemSpace, false>(sp, L, st, P, l, cnt);
+        if (n_comp == 3) pdf += L.general ? light_pdf<GmemSpace, false, true>(sp, L, st, P, l, cnt) : light_pdf<GmemSpace, false>(sp, L, st, P, l, cnt);
         y[0] = pdf * (1.0f / (float)n_comp);
     } else if (fn == RT_FN_SAMPLE_COSINE) {
         const float3 nn = f3(x[0], x[1], x[2]);
@@ -486,6 +558,15 @@ __global__ void __launch_bounds__(128) eval_kernel(const char* blob, const Scene
     } else if (fn == RT_FN_SAMPLE_LIGHT) {
         const float3 l = sample_light(sp, L, f3(x[0], x[1], x[2]), (int)x[3], x[4], x[5]);
         y[0] = l.x; y[1] = l.y; y[2] = l.z;
+    } else if (fn == RT_FN_SAMPLE_LIGHT_GEN) {
+        const uint32_t bits = (x[7] > 0.0f ? 0x80000000u : 0u) | ((uint32_t)(x[6] * 16777216.0f) << 7);     // sign | x01 (24 bits)
+        const float3 l = sample_light_gen(sp, L, f3(x[0], x[1], x[2]), (int)x[3], x[4], x[5], bits);
+        y[0] = l.x; y[1] = l.y; y[2] = l.z;
+    } else if (fn == RT_FN_DIELECTRIC) {
+        const float3 nn = f3(x[0], x[1], x[2]), v = f3(x[3], x[4], x[5]);
+        float3 l;
+        const bool refract = dielectric_sample(nn, v, dot(nn, v), x[6], x[7] > 0.0f, x[8], l);
+        y[0] = l.x; y[1] = l.y; y[2] = l.z; y[3] = refract ? 1.0f : 0.0f;
     } else if (fn == RT_FN_PHILOX) {
         const uint4 r = philox4x32_10(make_uint4(__float_as_uint(x[0]), __float_as_uint(x[1]), __float_as_uint(x[2]), RT_PHILOX_TAG),
                                       make_uint2(__float_as_uint(x[3]), 0u));

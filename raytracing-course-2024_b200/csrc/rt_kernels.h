@@ -42,14 +42,14 @@ struct KernelInfo { int block, blocks_per_sm, regs, smem_bytes, grid; };
 // while-while / phased trace bursts; cfg picks the v3 build (block size x min blocks per SM).  use_smem: stage the blob in shared memory.  Returns cudaError_t.
 cudaError_t launch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info);
 // How many lanes the render kernel keeps resident (grid * block) -- used to size the sample chunks.
-cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
+cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, bool general, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
 
 cudaError_t launch_sum_layers(const float4* layers, int n_layers, size_t n_pix, float4* accum, bool add, cudaStream_t stream);
 cudaError_t launch_resolve_u8(const float4* accum, size_t n_pix, uint8_t* rgb, cudaStream_t stream);
 cudaError_t launch_resolve_linear(const float4* accum, size_t n_pix, float* rgb, cudaStream_t stream);
 
 cudaError_t launch_trace_rays(const char* blob, const SceneLayout& L, const double* tri_d, uint32_t stack_entries, const double* rays, long long n,
-                              bool f64, int32_t* tri_id, double* t, cudaStream_t stream);
+                              bool f64, int32_t* tri_id, double* t, double* hits, cudaStream_t stream);
 cudaError_t launch_primary_rays(const Camera& cam, int W, int H, const int32_t* xy, const double* xi, long long n, double* rays, cudaStream_t stream);
 cudaError_t launch_eval(const char* blob, const SceneLayout& L, uint32_t stack_entries, int fn, const float* in, long long n, float* out, cudaStream_t stream);
 cudaError_t launch_ffma(int blocks, int threads, int iters, float* sink, cudaStream_t stream);

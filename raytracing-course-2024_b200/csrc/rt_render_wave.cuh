@@ -58,7 +58,9 @@ RT_DEV uint32_t pack_meta(int state, int depth, int attempt, uint32_t call) { re
 
 // MODE 0: while-while burst.  MODE 1: phased burst (box-pair steps while >= node_min lanes want one, else leaf phase).
 // BLOCK x MINB = resident threads per SM (occupancy / register budget trade-off, picked at run time from a few builds).
-template <class Space, bool STATS, int MODE, int BLOCK, int MINB>
+// GEN: general-primitive scenes (SceneLayout::general): leaves hold 64-byte primitive records (triangles, boxes, ellipsoids),
+// the infinite primitives are scanned when a ray retires (rendering.rs:215-224), vertices may be dielectric (own spec).
+template <class Space, bool STATS, int MODE, int BLOCK, int MINB, bool GEN = false>
 __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderArgs a) {
     constexpr int P = RT_POOL_SLOTS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -112,6 +114,16 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
         const float3 d = f3(fast_rcp(rs.inv.x), fast_rcp(rs.inv.y), fast_rcp(rs.inv.z));
         const float3 o = rs.od * d;
         const int skip_tri = pool.ldi(F_TRI, slot);
+        if (GEN) {
+            for (int i = first; i < first + n; ++i) {
+                float t, u, v;
+                const bool ok = prim_first_hit(load_prim(sp, L.prims, i), o, d, t, u, v);
+                if (STATS) cnt.tri_tests += 1;
+                if (ok && t < t_best && i != skip_tri) { t_best = t; hit_tri = i; pool.stf(F_U, slot, u); pool.stf(F_V, slot, v); }
+            }
+            cur = st.pop();
+            return;
+        }
         if (small_leaves) {                                                // leaves of 1-2 triangles: both tests side by side, one update
             const int second = first + (n > 1 ? 1 : 0);
             float t0, u0, v0, t1, u1, v1;
@@ -140,6 +152,17 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
             const unsigned fin = __ballot_sync(FULL, finished);
             if (fin != 0u) {
                 if (finished) {
+                    if (GEN && L.n_planes > 0) {                                  // infinite primitives after the BVH (rendering.rs:215-224)
+                        const float3 d = f3(fast_rcp(rs.inv.x), fast_rcp(rs.inv.y), fast_rcp(rs.inv.z));
+                        const float3 o = rs.od * d;
+                        const int skip_tri = pool.ldi(F_TRI, slot);
+                        for (int i = L.n_tris; i < L.n_tris + L.n_planes; ++i) {
+                            float t, u, v;
+                            const bool ok = prim_first_hit(load_prim(sp, L.prims, i), o, d, t, u, v);
+                            if (STATS) cnt.tri_tests += 1;
+                            if (ok && t < t_best && i != skip_tri) { t_best = t; hit_tri = i; pool.stf(F_U, slot, u); pool.stf(F_V, slot, v); }
+                        }
+                    }
                     pool.sti(F_TRI, slot, hit_tri);
                     pool.qst(1, (sq_head + sq_n + __popc(fin & lt_mask)) & (P - 1), slot);
                     slot = -1;
@@ -264,24 +287,32 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                     T = f3(1.f, 1.f, 1.f);
                     accepted = true;
                 } else if (live) {
-                    const uint32_t o16 = (uint32_t)tri * 16u;
                     const Material mat = load_material(sp, L, mat_id);
                     const float3 iv = pool.ld3(F_IX, s);                          // the ray direction is not stored: d = 1 / (1/d) (2^-22, shared-memory bound)
                     const float3 din = f3(fast_rcp(iv.x), fast_rcp(iv.y), fast_rcp(iv.z));
                     const float hu = pool.ldf(F_U, s), hv = pool.ldf(F_V, s);
-                    const float3 ng = f3(sp.ld4(L.sh_ng + o16));
-                    const float sgn = dot(ng, din) < 0.0f ? 1.0f : -1.0f;         // geometry.rs:115-126
-                    const float3 n = ng * sgn;
-                    const float3 dn1 = f3(sp.ld4(L.sh_dn1 + o16)), dn2 = f3(sp.ld4(L.sh_dn2 + o16));
-                    const float3 ns = (f3(n0) + dn1 * hu + dn2 * hv) * sgn;
-                    const float3 ta = f3(sp.ld4(L.tri_a + o16)), te1 = f3(sp.ld4(L.tri_e1 + o16)), te2 = f3(sp.ld4(L.tri_e2 + o16));
-                    const float3 Pt = fma3(din, -RT_EPS_F, fma3(te2, hv, fma3(te1, hu, ta)));   // :98
+                    const Vertex V = hit_vertex<Space, GEN>(sp, L, tri, n0, GEN ? pool.ld3(F_OX, s) : f3(0.f, 0.f, 0.f), din, hu, hv);
+                    const float3 n = V.n, ns = V.ns, Pt = V.P;
                     const float3 v = -din;
                     const float nv = dot(n, v);
+                    bool dielectric = false;
+                    float ior = 1.0f;
+                    if (GEN && L.has_dielectric) {
+                        const float4 m2 = sp.ld4(L.mat2 + (uint32_t)mat_id * 16u);
+                        dielectric = __float_as_int(m2.y) == RT_MAT_DIELECTRIC; ior = m2.x;
+                    }
+                    if (GEN && dielectric) {
+                        float3 l;
+                        const bool refract = dielectric_sample(n, v, nv, ior, V.outer, u01(rnd.x), l);
+                        if (STATS) ++c_attempts;
+                        if (refract) { ro = fma3(din, RT_EPS_F, V.surf); if (V.outer) T = T * mat.base; skip = V.flat ? tri : -1; }
+                        else { ro = Pt; skip = (V.flat || V.outer) ? tri : -1; }
+                        rd = l; attempt = 0; accepted = true;
+                    } else {
                     const float alpha = mat.roughness * mat.roughness, alpha2 = alpha * alpha;
                     const float g1v = ggx_g1(nv, alpha2);
                     float3 l; DirTerms terms;
-                    const float pdf = mix_sample_and_pdf<Space, STATS>(sp, L, st, a.n_comp, a.inv_n_comp, Pt, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
+                    const float pdf = mix_sample_and_pdf<Space, STATS, GEN>(sp, L, st, a.n_comp, a.inv_n_comp, Pt, n, v, nv, alpha, alpha2, g1v, rnd, l, terms, cnt);
                     ++attempt;
                     if (STATS) ++c_attempts;
                     if (pdf > 0.0f && dot(l, ns) > 0.0f) {                       // :107
@@ -289,12 +320,13 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                         const float3 f = brdf_eval(mat, d_chi, ggx_g1(terms.nl, alpha2), g1v, terms.nl, nv, terms.hl);
                         T = T * f * (terms.nl * fast_rcp(pdf));                  // :122
                         if (!finite3(T)) { if (STATS) ++c_nonfinite; state = ST_ENDED; }
-                        else { ro = Pt; rd = l; skip = terms.nl > 0.0f ? tri : -1; attempt = 0; accepted = true; }
+                        else { ro = Pt; rd = l; skip = (terms.nl > 0.0f && (V.flat || V.outer)) ? tri : -1; attempt = 0; accepted = true; }
                     } else if (attempt >= a.max_attempts || attempt >= 127) {
                         if (STATS) ++c_cap;
                         state = ST_ENDED;                                        // the path ends in the next round
                     } else {
                         state = ST_RETRY;
+                    }
                     }
                 }
                 if (accepted) {
@@ -362,10 +394,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
     }
 }
 
-template <class Space, bool STATS, int MODE, int BLOCK, int MINB>
+template <class Space, bool STATS, int MODE, int BLOCK, int MINB, bool GEN = false>
 static cudaError_t launch_wave_t(const RenderArgs& a, int device_sms, cudaStream_t stream, KernelInfo* info, bool launch, int* lanes) {
     const uint32_t smem = a.stack_entries * BLOCK * 4u + (IsSmem<Space>::value ? a.L.total_bytes : 0u) + (BLOCK / 32) * RT_POOL_WARP_BYTES;
-    auto kern = render_wave_kernel<Space, STATS, MODE, BLOCK, MINB>;
+    auto kern = render_wave_kernel<Space, STATS, MODE, BLOCK, MINB, GEN>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;
