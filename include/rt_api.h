@@ -95,7 +95,7 @@ typedef struct RtSceneInfo {
 typedef struct RtRenderParams {
     uint64_t seed;                    /* Philox key; the reference seeds xoshiro per row (rendering.rs:50-51) */
     int32_t sample_begin, sample_end; /* this call renders samples [begin,end) of [0,samples); 0,0 = all  */
-    int32_t max_attempts;             /* cap of the rejection loop rendering.rs:102-110 (0 = default 64)  */
+    int32_t max_attempts;             /* cap of the rejection loop rendering.rs:102-110 (0 = default 64; clamped to 127) */
     int32_t collect_stats;            /* 1: run the instrumented kernel and fill the work counters         */
     int32_t kernel_variant;           /* 0 = auto; else 10*kernel + placement (benchmarks / A-B tests):
                                          kernel 1 = per-lane megakernel, 2 / 3 = warp-local wavefront with while-while / phased trace bursts;
@@ -114,13 +114,18 @@ typedef struct RtStats {
     uint64_t tri_tests;               /* ray/triangle tests in nearest-hit queries                         */
     uint64_t light_tri_tests;         /* ray/triangle tests of the light pdf (distributions.rs:160-184)    */
     uint64_t attempt_cap_hits;        /* paths cut because max_attempts was reached (reference: spins)     */
-    uint64_t nonfinite_samples;       /* samples dropped because their radiance was NaN/Inf                */
+    uint64_t nonfinite_samples;       /* paths CUT at a vertex whose throughput became NaN/Inf: the radiance gathered before the cut is
+                                         kept and the sample counts (the reference would turn the whole pixel black, NaN -> 0)    */
     uint64_t kernel_launches;         /* CUDA kernels launched by this call                                */
     double   kernel_ms;               /* device time of the render kernels (CUDA events)                   */
     double   total_ms;                /* device time of the whole call incl. copies (CUDA events)          */
     int32_t  kernel;                  /* render kernel that ran: 1 = per-lane megakernel, 2 / 3 = warp-local wavefront (while-while / phased bursts) */
     int32_t  block_threads, blocks_per_sm, grid_blocks, regs_per_thread, smem_bytes_per_block;   /* its launch configuration */
     int32_t  scene_in_shared_memory;  /* 1: the scene blob was staged in shared memory by every block      */
+    int32_t  reserved2;
+    double   render_ms;               /* device time of the path-tracing kernel + layer sum (slowest device for rt_render_multi) */
+    double   reduce_ms;               /* device time of the cross-GPU framebuffer reduce (0 on one GPU)    */
+    double   resolve_ms;              /* device time of color_to_pixel                                     */
 } RtStats;
 
 /* ---- error reporting ------------------------------------------------------------------------------------ */

@@ -277,6 +277,14 @@ def intersect_shape(kind, params, o, d, upper=np.inf):
     return [(out[5 * k], out[5 * k + 1:5 * k + 4].copy(), bool(out[5 * k + 4])) for k in range(n)]
 
 
+def dielectric(n, v, ior_outer_u):
+    """[OWN SPEC] smooth dielectric direction choice: (cnt, 4) = direction xyz, refracted flag."""
+    n, v, iou = _d(n), _d(v), _d(ior_outer_u)
+    out = np.zeros((n.shape[0], 4))
+    lib().or_dielectric(_p(n), _p(v), _p(iou), C.c_int64(n.shape[0]), _p(out))
+    return out
+
+
 def quat_transform(q_ijkw, v, conjugate=False):
     q, v = _d(q_ijkw), _d(v)
     out = np.zeros(3)

@@ -722,6 +722,23 @@ static bool intersect_ray_with_scene(const Ray& ray, const Scene& sc, BvhInterse
     return found;
 }
 
+// [OWN SPEC] direction choice of the smooth dielectric (see get_ray_color): returns true for refraction.
+static bool dielectric_sample(V3 n, V3 v, Fp ior, bool outer_to_inner, Fp u, V3* dir) {
+    Fp eta = outer_to_inner ? 1.0 / ior : ior;
+    Fp cos1 = dot(n, v);
+    Fp sin2 = eta * std::sqrt(std::max(0.0, 1.0 - cos1 * cos1));
+    bool reflect = true;
+    Fp cos2 = 0.0;
+    if (sin2 < 1.0) {
+        cos2 = std::sqrt(1.0 - sin2 * sin2);
+        Fp r0 = powi2((eta - 1.0) / (eta + 1.0));
+        Fp refl = r0 + (1.0 - r0) * powi5(1.0 - cos1);
+        reflect = u < refl;
+    }
+    *dir = reflect ? normalize(reflect_vec(v, n)) : normalize((-v) * eta + n * (eta * cos1 - cos2));
+    return !reflect;
+}
+
 static V3 get_ray_color(const Ray& ray, const Scene& sc, int depth, Rng* rng, Counters* c) {   // :86-127
     if (depth <= 0) return v3(0, 0, 0);
     BvhIntersection bi;
@@ -739,23 +756,13 @@ static V3 get_ray_color(const Ray& ray, const Scene& sc, int depth, Rng* rng, Co
         // the outside index 1; Schlick reflectance; total internal reflection reflects; one uniform picks reflection (< R) or
         // refraction; the refracted ray starts EPS BEHIND the surface and is tinted by the base colour when it ENTERS.
         ++c->attempts;
-        Fp eta = bi.hit.is_outer_to_inner ? 1.0 / prim.ior : prim.ior;
-        Fp cos1 = dot(n, v);
-        Fp sin2 = eta * std::sqrt(std::max(0.0, 1.0 - cos1 * cos1));
-        Fp u = rng->gen_f64();
-        bool reflect = true;
-        Fp cos2 = 0.0;
-        if (sin2 < 1.0) {
-            cos2 = std::sqrt(1.0 - sin2 * sin2);
-            Fp r0 = powi2((eta - 1.0) / (eta + 1.0));
-            Fp refl = r0 + (1.0 - r0) * powi5(1.0 - cos1);
-            reflect = u < refl;
-        }
+        V3 dir;
+        bool reflect = !dielectric_sample(n, v, prim.ior, bi.hit.is_outer_to_inner, rng->gen_f64(), &dir);
         Ray next; V3 weight = v3(1, 1, 1);
-        if (reflect) { next.origin = corrected_point; next.direction = normalize(reflect_vec(v, n)); }
+        next.direction = dir;
+        if (reflect) next.origin = corrected_point;
         else {
             next.origin = ray.origin + ray.direction * (bi.hit.offset + EPS);
-            next.direction = normalize((-v) * eta + n * (eta * cos1 - cos2));
             if (bi.hit.is_outer_to_inner) weight = prim.material.base_color_factor;
         }
         return total + cmul(get_ray_color(next, sc, depth - 1, rng, c), weight);
@@ -1076,6 +1083,14 @@ int or_intersect_shape(int32_t kind, const double* params, const double* o, cons
     int n = intersect_all_points(r, p, upper, x);
     for (int k = 0; k < n; ++k) { out10[5 * k] = x[k].offset; wr3(out10 + 5 * k + 1, x[k].normal_geometry); out10[5 * k + 4] = x[k].is_outer_to_inner ? 1.0 : 0.0; }
     return n;
+}
+// [OWN SPEC] dielectric direction choice: n, v, (ior, outer, u) per sample -> dir xyz, refracted flag.
+void or_dielectric(const double* n, const double* v, const double* iou, int64_t cnt, double* out4) {
+    for (int64_t i = 0; i < cnt; ++i) {
+        V3 dir;
+        bool refr = dielectric_sample(rd3(n + 3 * i), rd3(v + 3 * i), iou[3 * i], iou[3 * i + 1] > 0.0, iou[3 * i + 2], &dir);
+        wr3(out4 + 4 * i, dir); out4[4 * i + 3] = refr ? 1.0 : 0.0;
+    }
 }
 void or_quat_transform(const double* q_ijkw, const double* v, int32_t conjugate, double* out) {
     Quat q = {q_ijkw[0], q_ijkw[1], q_ijkw[2], q_ijkw[3]};

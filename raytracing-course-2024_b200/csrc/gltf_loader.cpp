@@ -137,29 +137,42 @@ int ncomp_of(const std::string& t) {
 }
 int comp_size(int ct) { switch (ct) { case 5120: case 5121: return 1; case 5122: case 5123: return 2; case 5125: case 5126: return 4; default: return 0; } }
 
+// Every index / size of the document is taken through Value::index (non-negative integral < 2^53, else the file is rejected -- the
+// gltf crate's deserialiser rejects such files too) and every range check is written without overflow.
 bool accessor_view(const Doc& d, long long idx, AccessorView* v, std::string* why) {
     const rtjson::Value* accs = d.root->get("accessors");
     if (!accs || idx < 0 || (size_t)idx >= accs->size()) { *why = "accessor index out of range"; return false; }
     const rtjson::Value& acc = accs->at((size_t)idx);
     if (acc.has("sparse")) { *why = "sparse accessors are not supported"; return false; }
-    long long bvi = acc.integer("bufferView", -1);
+    const long long bvi = acc.index("bufferView");
     const rtjson::Value* bvs = d.root->get("bufferViews");
-    if (!bvs || bvi < 0 || (size_t)bvi >= bvs->size()) { *why = "accessor without bufferView"; return false; }
+    if (!bvs || bvi < 0 || (size_t)bvi >= bvs->size()) { *why = "accessor without a valid bufferView"; return false; }
     const rtjson::Value& bv = bvs->at((size_t)bvi);
-    long long bi = bv.integer("buffer", -1);
+    const long long bi = bv.index("buffer");
     if (bi < 0 || (size_t)bi >= d.buffers.size()) { *why = "bufferView.buffer out of range"; return false; }
-    v->component_type = (int)acc.integer("componentType", 0);
+    const long long ct = acc.index("componentType");
+    v->component_type = ct >= 0 && ct < 65536 ? (int)ct : 0;
     v->ncomp = ncomp_of(acc.string("type", ""));
-    int cs = comp_size(v->component_type);
+    const int cs = comp_size(v->component_type);
     if (cs == 0 || v->ncomp == 0) { *why = "unknown accessor type"; return false; }
-    size_t off = (size_t)bv.integer("byteOffset", 0) + (size_t)acc.integer("byteOffset", 0);
-    size_t stride = (size_t)bv.integer("byteStride", 0);
-    if (stride == 0) stride = (size_t)cs * (size_t)v->ncomp;
-    v->count = (size_t)acc.integer("count", 0);
-    v->stride = stride;
+    const long long bv_off = bv.has("byteOffset") ? bv.index("byteOffset") : 0, acc_off = acc.has("byteOffset") ? acc.index("byteOffset") : 0;
+    const long long bv_stride = bv.has("byteStride") ? bv.index("byteStride") : 0, count = acc.index("count");
+    const long long bv_len = bv.has("byteLength") ? bv.index("byteLength") : -1;
+    if (bv_off < 0 || acc_off < 0 || bv_stride < 0 || count < 0 || (bv.has("byteLength") && bv_len < 0)) { *why = "accessor / bufferView with a negative or non-integral size"; return false; }
     const std::string& buf = d.buffers[(size_t)bi];
-    if (v->count > 0 && off + stride * (v->count - 1) + (size_t)cs * (size_t)v->ncomp > buf.size()) { *why = "accessor exceeds its buffer"; return false; }
-    v->base = (const unsigned char*)buf.data() + off;
+    const size_t elem = (size_t)cs * (size_t)v->ncomp;
+    const size_t stride = bv_stride == 0 ? elem : (size_t)bv_stride;
+    if (stride < elem && bv_stride != 0) { *why = "bufferView.byteStride smaller than the element"; return false; }
+    // the view [bv_off, bv_off + bv_len) must lie inside the buffer, the accessor inside the view
+    if ((size_t)bv_off > buf.size()) { *why = "bufferView starts past its buffer"; return false; }
+    size_t avail = buf.size() - (size_t)bv_off;
+    if (bv_len >= 0) { if ((size_t)bv_len > avail) { *why = "bufferView exceeds its buffer"; return false; } avail = (size_t)bv_len; }
+    if ((size_t)acc_off > avail) { *why = "accessor starts past its bufferView"; return false; }
+    avail -= (size_t)acc_off;
+    if (count > 0 && (avail < elem || (size_t)(count - 1) > (avail - elem) / stride)) { *why = "accessor exceeds its bufferView"; return false; }
+    v->count = (size_t)count;
+    v->stride = stride;
+    v->base = (const unsigned char*)buf.data() + (size_t)bv_off + (size_t)acc_off;
     return true;
 }
 
@@ -175,7 +188,7 @@ struct Builder {
     void material_of(const rtjson::Value& prim, double mat[5], double emission[3]) {
         const rtjson::Value* m = nullptr;
         const rtjson::Value* mats = d.root->get("materials");
-        long long mi = prim.integer("material", -1);
+        long long mi = prim.index("material");
         if (mats && mi >= 0 && (size_t)mi < mats->size()) m = &mats->at((size_t)mi);
         float base[3] = {1.0f, 1.0f, 1.0f}, metallic = 1.0f, rough = 1.0f, ef[3] = {0.0f, 0.0f, 0.0f};
         double strength = 1.0;
@@ -250,7 +263,7 @@ struct Builder {
 
         if (node.has("camera")) {
             const rtjson::Value* cams = d.root->get("cameras");
-            long long ci = node.integer("camera", -1);
+            long long ci = node.index("camera");
             if (!cams || ci < 0 || (size_t)ci >= cams->size()) return fail(RT_ERR_FORMAT, "camera index out of range");
             const rtjson::Value& cam = cams->at((size_t)ci);
             const rtjson::Value* persp = cam.get("perspective");
@@ -270,7 +283,7 @@ struct Builder {
 
         if (node.has("mesh")) {
             const rtjson::Value* meshes = d.root->get("meshes");
-            long long mi = node.integer("mesh", -1);
+            long long mi = node.index("mesh");
             if (!meshes || mi < 0 || (size_t)mi >= meshes->size()) return fail(RT_ERR_FORMAT, "mesh index out of range");
             const rtjson::Value* prims = meshes->at((size_t)mi).get("primitives");
             if (!prims || prims->size() == 0) return fail(RT_ERR_FORMAT, "mesh without primitives");
@@ -281,12 +294,12 @@ struct Builder {
             if (!attrs || !attrs->has("POSITION")) return fail(RT_ERR_FORMAT, "Missing positions!");
             std::string why;
             AccessorView iv, pv, nv;
-            if (!accessor_view(d, prim.integer("indices", -1), &iv, &why)) return fail(RT_ERR_FORMAT, "indices: " + why);
-            if (!accessor_view(d, attrs->integer("POSITION", -1), &pv, &why)) return fail(RT_ERR_FORMAT, "POSITION: " + why);
+            if (!accessor_view(d, prim.index("indices"), &iv, &why)) return fail(RT_ERR_FORMAT, "indices: " + why);
+            if (!accessor_view(d, attrs->index("POSITION"), &pv, &why)) return fail(RT_ERR_FORMAT, "POSITION: " + why);
             if (pv.component_type != 5126 || pv.ncomp != 3) return fail(RT_ERR_FORMAT, "POSITION must be float VEC3");
             bool has_normals = attrs->has("NORMAL");
             if (has_normals) {
-                if (!accessor_view(d, attrs->integer("NORMAL", -1), &nv, &why)) return fail(RT_ERR_FORMAT, "NORMAL: " + why);
+                if (!accessor_view(d, attrs->index("NORMAL"), &nv, &why)) return fail(RT_ERR_FORMAT, "NORMAL: " + why);
                 if (nv.component_type != 5126 || nv.ncomp != 3) return fail(RT_ERR_FORMAT, "NORMAL must be float VEC3");
             }
             if (iv.component_type != 5121 && iv.component_type != 5123 && iv.component_type != 5125) return fail(RT_ERR_FORMAT, "indices must be u8/u16/u32");
@@ -346,7 +359,11 @@ struct Builder {
         }
         if (const rtjson::Value* ch = node.get("children"))                               // :245-255
             for (size_t k = 0; k < ch->size(); ++k)
-                if (!read_primitives((size_t)ch->at(k).num, m, current_rotation)) return false;
+            {
+                const long long ci = ch->at(k).as_index();
+                if (ci < 0) return fail(RT_ERR_FORMAT, "node.children entry is not a non-negative integer");
+                if (!read_primitives((size_t)ci, m, current_rotation)) return false;
+            }
         --depth_guard;
         return true;
     }

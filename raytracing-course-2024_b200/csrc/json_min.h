@@ -38,6 +38,13 @@ struct Value {
     }
     double number(const char* key, double dflt) const { const Value* v = get(key); return (v && v->kind == Number) ? v->num : dflt; }
     long long integer(const char* key, long long dflt) const { const Value* v = get(key); return (v && v->kind == Number) ? (long long)v->num : dflt; }
+    // Non-negative integral number below 2^53, or -1 when the key is absent (absent_ok) -- anything else (negative, fractional, NaN,
+    // huge, not a number) is -2: the caller rejects the file instead of casting an out-of-range double (undefined behaviour).
+    long long index(const char* key) const { const Value* v = get(key); return v ? v->as_index() : -1; }
+    long long as_index() const {
+        if (kind != Number || !(num >= 0.0) || !(num < 9007199254740992.0) || num != (double)(long long)num) return -2;
+        return (long long)num;
+    }
     std::string string(const char* key, const std::string& dflt) const { const Value* v = get(key); return (v && v->kind == String) ? v->str : dflt; }
 };
 
@@ -59,7 +66,11 @@ private:
     void ws() { while (p_ < s_.size() && (s_[p_] == ' ' || s_[p_] == '\t' || s_[p_] == '\n' || s_[p_] == '\r')) ++p_; }
     bool lit(const char* w) { size_t n = std::strlen(w); if (s_.compare(p_, n, w) == 0) { p_ += n; return true; } return false; }
 
+    int depth_ = 0;
+    struct DepthGuard { int& d; explicit DepthGuard(int& x) : d(x) { ++d; } ~DepthGuard() { --d; } };
     ValuePtr value() {
+        DepthGuard guard(depth_);
+        if (depth_ > 256) fail("JSON nested deeper than 256 levels");      // recursion bound: a hostile file must not overflow the stack
         ws();
         if (p_ >= s_.size()) fail("unexpected end");
         ValuePtr v = std::make_shared<Value>();

@@ -1,6 +1,8 @@
 // main.cpp -- the `raytracing-engine` CLI with the reference's argv (src/main.rs:28-73, run.sh:2):
-//     raytracing-engine <scene.gltf> <width> <height> <samples> <out.ppm> [png_basename]
-// Scene ingest, rendering and output all go through the C ABI (include/rt_api.h); this file is what main.rs
+//     raytracing-engine <scene.gltf|scene.txt> <width> <height> <samples> <out.ppm> [png_basename]
+//     raytracing-engine <scene.txt> <out.ppm>                       (the text era's form: DIMENSIONS / SAMPLES come from the file)
+// A ".txt" scene is the course's text format (rt_scene_load_text: own spec, reference HEAD dropped its parser, main.rs:48);
+// width / height / samples <= 0 keep the file's DIMENSIONS / SAMPLES.  Scene ingest, rendering and output all go through the C ABI (include/rt_api.h); this file is what main.rs
 // becomes once render_scene is the B200 library.  Differences from the reference, on purpose:
 //   * errors are reported and the exit code is non-zero (the reference panics);
 //   * the PPM is truncated, not appended to (main.rs:62-66 opens with append(true), which stacks a second image
@@ -20,13 +22,13 @@
 static long long env_ll(const char* name, long long dflt) { const char* v = std::getenv(name); return v && *v ? std::atoll(v) : dflt; }
 
 int main(int argc, char** argv) {
-    if (argc < 6) {
-        std::fprintf(stderr, "usage: %s <scene.gltf> <width> <height> <samples> <out.ppm> [png_basename]\n", argv[0]);
+    if (argc != 3 && argc < 6) {
+        std::fprintf(stderr, "usage: %s <scene.gltf|scene.txt> <width> <height> <samples> <out.ppm> [png_basename]\n       %s <scene.txt> <out.ppm>\n", argv[0], argv[0]);
         return 2;
     }
     const char* input_scene = argv[1];
-    const int width = std::atoi(argv[2]), height = std::atoi(argv[3]), samples = std::atoi(argv[4]);
-    const char* output_ppm = argv[5];
+    int width = argc == 3 ? 0 : std::atoi(argv[2]), height = argc == 3 ? 0 : std::atoi(argv[3]), samples = argc == 3 ? 0 : std::atoi(argv[4]);
+    const char* output_ppm = argc == 3 ? argv[2] : argv[5];
     const int device = (int)env_ll("RT_DEVICE", 0);
 
     int n_gpus = (int)env_ll("RT_GPUS", 1);
@@ -34,16 +36,23 @@ int main(int argc, char** argv) {
     std::vector<RtScene*> scenes((size_t)n_gpus, nullptr);
     auto destroy_all = [&]() { for (RtScene* s : scenes) if (s) rt_scene_destroy(s); };
     for (int g = 0; g < n_gpus; ++g) {                                                             // main.rs:45-47 on every device
-        if (rt_scene_load_gltf(input_scene, width, height, samples, device + g, &scenes[(size_t)g]) != RT_OK) {
+        if (rt_scene_load(input_scene, width, height, samples, device + g, &scenes[(size_t)g]) != RT_OK) {
             std::fprintf(stderr, "error: %s\n", rt_last_error());
             destroy_all();
             return 1;
         }
     }
-    rt_multi_init(scenes.data(), n_gpus);        // NCCL communicators are part of the set-up, like the BVH build (main.rs:45-47)
+    if (rt_multi_init(scenes.data(), n_gpus) != RT_OK) {   // NCCL communicators are part of the set-up, like the BVH build (main.rs:45-47)
+        std::fprintf(stderr, "error: %s\n", rt_last_error());
+        destroy_all();
+        return 1;
+    }
     RtScene* scene = scenes[0];
     RtSceneInfo info;
     rt_scene_info(scene, &info);
+    RtSceneDesc desc;
+    rt_scene_get_desc(scene, &desc);                                                               // a text scene brings its own DIMENSIONS / SAMPLES
+    width = desc.width; height = desc.height; samples = desc.samples;
     std::printf("Scene finite primitives: %d, light sources: %d\n", info.n_tris, info.n_lights);   // main.rs:49-53
 
     std::vector<uint8_t> rendered((size_t)width * (size_t)height * 3);

@@ -10,12 +10,23 @@
 #include <cstring>
 #include <limits>
 #include <map>
+#include <mutex>
 #include <string>
 #include <vector>
 
 #include "../../include/rt_api.h"
 #include "host_scene.h"
 #include "rt_kernels.h"
+
+// ABI layout guards: rust/rt-sys/src/lib.rs asserts the same numbers (size_of / offset_of), tests/test_rust_binding.py compares the
+// field lists -- the binding the reference's render_scene (src/rendering.rs:21, call site src/main.rs:55) links against must not drift.
+#include <cstddef>
+static_assert(sizeof(RtSceneDesc) == 192 && offsetof(RtSceneDesc, bg_color) == 16 && offsetof(RtSceneDesc, camera_fov_x) == 136 &&
+              offsetof(RtSceneDesc, n_tris) == 152 && offsetof(RtSceneDesc, tri_v) == 160, "RtSceneDesc layout");
+static_assert(sizeof(RtSceneDesc2) == 232 && offsetof(RtSceneDesc2, shape_kind) == 192, "RtSceneDesc2 layout");
+static_assert(sizeof(RtSceneInfo) == 72 && offsetof(RtSceneInfo, device_bytes) == 40 && offsetof(RtSceneInfo, bvh_build_ms) == 56, "RtSceneInfo layout");
+static_assert(sizeof(RtRenderParams) == 40 && offsetof(RtRenderParams, sample_begin) == 8, "RtRenderParams layout");
+static_assert(sizeof(RtStats) == 152 && offsetof(RtStats, kernel_ms) == 80 && offsetof(RtStats, kernel) == 96 && offsetof(RtStats, render_ms) == 128, "RtStats layout");
 
 namespace {
 
@@ -56,7 +67,7 @@ struct RtScene {
     unsigned int* work_counter = nullptr;
     unsigned long long* stats_dev = nullptr;
     cudaStream_t stream = nullptr;
-    cudaEvent_t ev[4] = {nullptr, nullptr, nullptr, nullptr};
+    cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
 };
 
 namespace {
@@ -411,7 +422,7 @@ int upload_scene(RtScene* s) {
     CUDA_TRY(cudaSetDevice(s->device));
     CUDA_TRY(cudaDeviceGetAttribute(&s->sms, cudaDevAttrMultiProcessorCount, s->device));
     CUDA_TRY(cudaStreamCreateWithFlags(&s->stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 4; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
+    for (int i = 0; i < 5; ++i) CUDA_TRY(cudaEventCreate(&s->ev[i]));
     CUDA_TRY(cudaMalloc((void**)&s->blob_dev, s->blob_host.size()));
     CUDA_TRY(cudaMemcpy(s->blob_dev, s->blob_host.data(), s->blob_host.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&s->work_counter, sizeof(unsigned int)));
@@ -462,7 +473,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     fill_camera(h, &a.cam);
     for (int k = 0; k < 3; ++k) a.bg[k] = (float)h.bg_color[k];
     a.W = h.width; a.H = h.height; a.ray_depth = h.ray_depth;
-    a.max_attempts = p->max_attempts > 0 ? p->max_attempts : 64;
+    a.max_attempts = std::min(p->max_attempts > 0 ? p->max_attempts : 64, 127);   // every kernel: the wavefront kernel keeps the attempt count in 7 bits
     a.n_comp = s->L.n_lights > 0 ? 3 : 2;                     // rendering.rs:23-31
     a.inv_n_comp = 1.0f / (float)a.n_comp;
     a.s_begin = s0; a.s_end = s1;
@@ -494,6 +505,17 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
         return fail(RT_ERR_LIMIT, "ray_depth x max_attempts exceeds the 14-bit Philox call counter of the wavefront kernel (lower max_attempts, or kernel_variant 10)");
     if (plan->variant != 1 && h.ray_depth > 255) return fail(RT_ERR_LIMIT, "ray_depth above 255 (the wavefront kernel packs the remaining depth in 8 bits; kernel_variant 10 has no limit)");
 
+    if (h.ray_depth == 0) {                                    // rendering.rs:93-95: recursion_depth <= 0 is black, the scene is never looked at
+        a.chunk_size = s1 - s0; a.n_chunks = 1; a.n_pix_items = 0; a.total_items = 0;
+        const size_t n_pix0 = (size_t)h.width * (size_t)h.height;
+        int rc0 = ensure(&s->layers, &s->layers_cap, n_pix0);
+        if (rc0 != RT_OK) return rc0;
+        a.layers = s->layers;
+        if (plan->stats) CUDA_TRY(cudaMemsetAsync(s->stats_dev, 0, sizeof(unsigned long long) * rtd::RT_N_STATS, stream));
+        CUDA_TRY(rtd::launch_black_layer(s->layers, h.width, h.height, a.tiles_x, a.shard_index, a.shard_count, (float)(s1 - s0), stream));
+        std::memset(ki, 0, sizeof(*ki));
+        return RT_OK;
+    }
     plan->cfg = env_int("RT_WAVE_CFG", 2);
     // sample chunks: enough (pixel, chunk) items to keep every resident path slot busy many times over
     int lanes = 0;
@@ -680,7 +702,7 @@ void rt_scene_destroy(RtScene* s) {
     if (s->stream || s->blob_dev) cudaSetDevice(s->device);
     cudaFree(s->blob_dev); cudaFree(s->tri_d_dev); cudaFree(s->layers); cudaFree(s->accum); cudaFree(s->rgb_dev); cudaFree(s->lin_dev);
     cudaFree(s->work_counter); cudaFree(s->stats_dev);
-    for (int i = 0; i < 4; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
+    for (int i = 0; i < 5; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
 }
@@ -749,6 +771,7 @@ int rt_render(RtScene* s, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st
     if ((rc = ensure(&s->accum, &s->accum_cap, n_pix)) != RT_OK) return rc;
     if ((rc = ensure(&s->rgb_dev, &s->rgb_cap, n_pix * 3)) != RT_OK) return rc;
     CUDA_TRY(rtd::launch_sum_layers(s->layers, plan.args.n_chunks, n_pix, s->accum, false, stream));
+    CUDA_TRY(cudaEventRecord(s->ev[4], stream));
     CUDA_TRY(rtd::launch_resolve_u8(s->accum, n_pix, s->rgb_dev, stream));
     CUDA_TRY(cudaEventRecord(s->ev[2], stream));
     CUDA_TRY(cudaMemcpyAsync(rgb_out, s->rgb_dev, n_pix * 3, cudaMemcpyDeviceToHost, stream));
@@ -756,9 +779,10 @@ int rt_render(RtScene* s, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st
     CUDA_TRY(cudaStreamSynchronize(stream));
     if ((rc = collect_stats(s, plan, ki, st, 3, stream)) != RT_OK) return rc;
     if (st) {
-        float k = 0, t = 0;
+        float k = 0, t = 0, r = 0, v = 0;
         cudaEventElapsedTime(&k, s->ev[1], s->ev[2]); cudaEventElapsedTime(&t, s->ev[0], s->ev[3]);
-        st->kernel_ms = k; st->total_ms = t;
+        cudaEventElapsedTime(&r, s->ev[0], s->ev[4]); cudaEventElapsedTime(&v, s->ev[4], s->ev[2]);
+        st->kernel_ms = k; st->total_ms = t; st->render_ms = r; st->reduce_ms = 0.0; st->resolve_ms = v;
     }
     return RT_OK;
 }
@@ -826,6 +850,10 @@ struct NcclApi {
     const char* (*GetErrorString)(int) = nullptr;
     bool ok = false;
 };
+// One lock serialises libnccl loading, communicator (re)creation and every multi-GPU frame of the process: the communicator
+// cache is process-wide state and NCCL group calls on one communicator set must not interleave between host threads.  Distinct
+// scenes used through the single-GPU entry points from distinct threads never touch it.
+std::mutex& multi_gpu_mutex() { static std::mutex m; return m; }
 NcclApi& nccl_api() {
     static NcclApi api;
     static bool tried = false;
@@ -870,6 +898,7 @@ bool ensure_comms(const std::vector<int>& devs) {
 
 int rt_multi_init(RtScene* const* scenes, int32_t n) {
     if (!scenes || n < 1) return fail(RT_ERR_INVALID, "bad argument");
+    std::lock_guard<std::mutex> lock(multi_gpu_mutex());
     std::vector<int> devs;
     for (int g = 0; g < n; ++g) { if (!scenes[g] || !scenes[g]->blob_dev) return fail(RT_ERR_CUDA, "rt_multi_init: every scene must live on a CUDA device"); devs.push_back(scenes[g]->device); }
     if (n > 1 && ensure_comms(devs)) {                      // first collective = connection set-up: do it now, on a few floats
@@ -896,9 +925,27 @@ int rt_multi_init(RtScene* const* scenes, int32_t n) {
     return RT_OK;
 }
 
+namespace {
+int render_multi_locked(RtScene* const* scenes, int32_t n, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st);
+}
 int rt_render_multi(RtScene* const* scenes, int32_t n, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st) {
     if (!scenes || n < 1 || !rgb_out) return fail(RT_ERR_INVALID, "bad argument");
     if (n == 1) return rt_render(scenes[0], p, rgb_out, st);
+    std::lock_guard<std::mutex> lock(multi_gpu_mutex());
+    const int rc = render_multi_locked(scenes, n, p, rgb_out, st);
+    if (rc != RT_OK) {
+        // a failure part-way leaves kernels / copies in flight on the devices launched so far: drain every stream before the
+        // caller may free or reuse its buffers (rgb_out is the target of an asynchronous copy), keeping the first error message
+        const std::string first = g_last_error;
+        for (int g = 0; g < n; ++g)
+            if (scenes[g] && scenes[g]->stream) { cudaSetDevice(scenes[g]->device); cudaStreamSynchronize(scenes[g]->stream); }
+        cudaGetLastError();
+        g_last_error = first;
+    }
+    return rc;
+}
+namespace {
+int render_multi_locked(RtScene* const* scenes, int32_t n, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st) {
     RtScene* s0 = scenes[0];
     if (!s0) return fail(RT_ERR_INVALID, "null scene");
     const int W = s0->host.width, H = s0->host.height, S = s0->host.samples;
@@ -945,6 +992,7 @@ int rt_render_multi(RtScene* const* scenes, int32_t n, const RtRenderParams* p, 
         } else {
             CUDA_TRY(cudaMemsetAsync(s->accum, 0, n_pix * sizeof(float4), s->stream));
         }
+        if (g == 0) CUDA_TRY(cudaEventRecord(s->ev[1], s->stream));
     }
     // 2. ONE reduce(sum) of the W*H*4 accumulators to device 0 (NVLink), the only communication of the frame
     NcclApi& nc = nccl_api();
@@ -975,6 +1023,7 @@ int rt_render_multi(RtScene* const* scenes, int32_t n, const RtRenderParams* p, 
     CUDA_TRY(cudaSetDevice(s0->device));
     int rc = ensure(&s0->rgb_dev, &s0->rgb_cap, n_pix * 3);
     if (rc != RT_OK) return rc;
+    CUDA_TRY(cudaEventRecord(s0->ev[4], s0->stream));
     CUDA_TRY(rtd::launch_resolve_u8(s0->accum, n_pix, s0->rgb_dev, s0->stream));
     CUDA_TRY(cudaEventRecord(s0->ev[2], s0->stream));
     CUDA_TRY(cudaMemcpyAsync(rgb_out, s0->rgb_dev, n_pix * 3, cudaMemcpyDeviceToHost, s0->stream));
@@ -997,10 +1046,14 @@ int rt_render_multi(RtScene* const* scenes, int32_t n, const RtRenderParams* p, 
         CUDA_TRY(cudaSetDevice(s0->device));
         cudaEventElapsedTime(&k, s0->ev[0], s0->ev[2]); cudaEventElapsedTime(&t, s0->ev[0], s0->ev[3]);
         total.kernel_ms = k; total.total_ms = t;
+        float r0 = 0, r1 = 0, r2 = 0;                                         // phases on device 0's clock: its render, the reduce, the resolve
+        cudaEventElapsedTime(&r0, s0->ev[0], s0->ev[1]); cudaEventElapsedTime(&r1, s0->ev[1], s0->ev[4]); cudaEventElapsedTime(&r2, s0->ev[4], s0->ev[2]);
+        total.render_ms = r0; total.reduce_ms = r1; total.resolve_ms = r2;
         *st = total;
     }
     return RT_OK;
 }
+}  // namespace
 
 int rt_resolve_device(const float* accum_dev, int32_t width, int32_t height, uint8_t* rgb_dev, void* stream_v) {
     if (!accum_dev || !rgb_dev || width <= 0 || height <= 0) return fail(RT_ERR_INVALID, "bad argument");

@@ -290,11 +290,20 @@ RT_DEV float3 prim_s(const PrimRec& R) { return f3(R.r1.w, R.r2.w, R.r3.w); }
 RT_DEV float3 prim_to_local(const PrimRec& R, float3 v) { return f3(dot(f3(R.r0), v), dot(f3(R.r1), v), dot(f3(R.r2), v)); }   // q.conjugate() * v
 RT_DEV float3 prim_to_world(const PrimRec& R, float3 v) { return f3(R.r0) * v.x + f3(R.r1) * v.y + f3(R.r2) * v.z; }          // q * v
 
+// Face of a box hit: the slab that produced it, overridden by the reference's `s - |p| < EPS` cascade (geometry.rs:161-169: x
+// before y before z) when the hit point lies within EPS of a higher-priority face -- the same answer as the reference at edges
+// and corners, and a robust one (the slab) in the interior of a face, where FP32 could not resolve `s - |p| < 1e-5` reliably.
+RT_DEV int box_face(float3 s, float3 ol, float3 dl, float t, int slab_axis) {
+    const float3 p = fma3(dl, t, ol);
+    if (s.x - fabsf(p.x) < RT_EPS_F) return 0;
+    if (slab_axis == 2 && s.y - fabsf(p.y) < RT_EPS_F) return 1;
+    return slab_axis;
+}
+
 // FIRST hit of a primitive = what competes in the nearest-hit query (points.0[0], bvh.rs:269) and what
 // intersect_ray_with_object3d returns (geometry.rs:51-58,196-223).  Out: t; triangles: (u, v) barycentrics; others: u = t,
 // v = aux bits (box: axis 0..2 of the face; RT_AUX_EXIT when the ray leaves the solid / hits the back of a plane).
-//   box       geometry.rs:140-194: object-space slabs, entry hit if t_min > 0, else the exit hit if t_max > 0.  The face is the
-//             slab that produced the hit (x, y, z priority on ties, like the `s - |p| < EPS` cascade of :161-169 at edges).
+//   box       geometry.rs:140-194: object-space slabs, entry hit if t_min > 0, else the exit hit if t_max > 0.  Face: box_face.
 //   ellipsoid own spec: |(o + t d)/r|^2 = 1 around the closest approach (no cancellation in FP32); outside -> entry root if the
 //             ray approaches, inside -> exit root.  Same roots as the oracle's half-b form.
 //   plane     own spec: t = n.(pos - o) / n.d with the world normal n = R s.
@@ -324,7 +333,8 @@ RT_DEV bool prim_first_hit(const PrimRec& R, float3 o, float3 d, float& t, float
         if (!(tmin <= tmax)) return false;
         const bool entry = tmin > 0.0f;
         t = entry ? tmin : tmax;
-        const int axis = entry ? ((nx >= ny && nx >= nz) ? 0 : (ny >= nz ? 1 : 2)) : ((fx <= fy && fx <= fz) ? 0 : (fy <= fz ? 1 : 2));
+        const int slab = entry ? ((nx >= ny && nx >= nz) ? 0 : (ny >= nz ? 1 : 2)) : ((fx <= fy && fx <= fz) ? 0 : (fy <= fz ? 1 : 2));
+        const int axis = box_face(s, ol, dl, t, slab);
         u = t; v = __int_as_float(axis | (entry ? 0 : RT_AUX_EXIT));
         return t > 0.0f;
     }
@@ -555,8 +565,10 @@ RT_DEV float light_prim_pdf(const Space& sp, const SceneLayout& L, int i, float3
         const float tmin = max3f(nx, ny, nz), tmax = min3f(fx, fy, fz);
         if (!(tmin <= tmax) || !(tmax > 0.0f)) return 0.0f;
         const float local_pdf = fast_rcp(8.0f * (s.x * s.y + s.y * s.z + s.z * s.x));
-        const float dn = fabsf((nx >= ny && nx >= nz) ? dl.x : (ny >= nz ? dl.y : dl.z));
-        const float df = fabsf((fx <= fy && fx <= fz) ? dl.x : (fy <= fz ? dl.y : dl.z));
+        const int an = box_face(s, ol, dl, tmin, (nx >= ny && nx >= nz) ? 0 : (ny >= nz ? 1 : 2));
+        const int af = box_face(s, ol, dl, tmax, (fx <= fy && fx <= fz) ? 0 : (fy <= fz ? 1 : 2));
+        const float dn = fabsf(an == 0 ? dl.x : (an == 1 ? dl.y : dl.z));
+        const float df = fabsf(af == 0 ? dl.x : (af == 1 ? dl.y : dl.z));
         float sum = tmax * tmax * fast_rcp(df);
         if (tmin > 0.0f) sum += tmin * tmin * fast_rcp(dn);
         return local_pdf * sum;

@@ -261,14 +261,14 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS) render_kernel(const R
                     const float d_chi = terms.nh > 0.0f ? terms.d_nochi : 0.0f;      // chi_plus(hn) :164
                     const float3 f = brdf_eval(mat, d_chi, ggx_g1(terms.nl, alpha2), g1v, terms.nl, nv, terms.hl);   // :121
                     T = T * f * (terms.nl * fast_rcp(pdf));                          // :122
+                    if (!finite3(T)) { if (STATS) ++c_nonfinite; end_path = true; }  // same policy as the wavefront kernel: cut here, keep what was gathered
                     o = P; d = l;
                     skip_tri = terms.nl > 0.0f ? hit.tri : -1;
                 }
             }
         }
         if (end_path) {
-            if (finite3(Ls)) acc = acc + Ls;
-            else if (STATS) ++c_nonfinite;
+            acc = acc + Ls;
             acc_n += 1.0f;
             alive = false;
         }
@@ -351,6 +351,17 @@ __global__ void sum_layers_kernel(const float4* __restrict__ layers, int n_layer
     }
 }
 
+// ray_depth == 0: get_ray_color returns black before it looks at the scene (rendering.rs:93-95) -- every owned pixel receives
+// n_samples samples of zero radiance, no ray is traced.
+__global__ void black_layer_kernel(float4* __restrict__ layer, int W, int H, uint32_t tiles_x, uint32_t shard_index, uint32_t shard_count, float n_samples) {
+    const size_t n_pix = (size_t)W * (size_t)H;
+    for (size_t p = (size_t)blockIdx.x * blockDim.x + threadIdx.x; p < n_pix; p += (size_t)gridDim.x * blockDim.x) {
+        const uint32_t x = (uint32_t)(p % (size_t)W), y = (uint32_t)(p / (size_t)W);
+        const uint32_t tile = (y >> 2) * tiles_x + (x >> 3);
+        layer[p] = make_float4(0.f, 0.f, 0.f, tile % shard_count == shard_index ? n_samples : 0.f);
+    }
+}
+
 // color_to_pixel (rendering.rs:250-262) in f64 like the reference: mean -> aces_tonemap (:236-248) -> saturate ->
 // powf(1/2.2) -> round (half away from zero) -> saturating `as u8` (NaN -> 0).
 __device__ __forceinline__ unsigned char tonemap_channel(double x) {
@@ -380,6 +391,10 @@ __global__ void resolve_linear_kernel(const float4* __restrict__ accum, size_t n
     }
 }
 static int grid_for(size_t n, int block) { size_t g = (n + (size_t)block - 1) / (size_t)block; return (int)(g > 148u * 16u ? 148u * 16u : (g ? g : 1)); }
+cudaError_t launch_black_layer(float4* layer, int W, int H, uint32_t tiles_x, uint32_t shard_index, uint32_t shard_count, float n_samples, cudaStream_t stream) {
+    black_layer_kernel<<<grid_for((size_t)W * (size_t)H, 256), 256, 0, stream>>>(layer, W, H, tiles_x, shard_index, shard_count, n_samples);
+    return cudaGetLastError();
+}
 cudaError_t launch_sum_layers(const float4* layers, int n_layers, size_t n_pix, float4* accum, bool add, cudaStream_t stream) {
     sum_layers_kernel<<<grid_for(n_pix, 256), 256, 0, stream>>>(layers, n_layers, n_pix, accum, add ? 1 : 0);
     return cudaGetLastError();

@@ -44,6 +44,7 @@ cudaError_t launch_render(const RenderArgs& a, int variant, int cfg, bool use_sm
 // How many lanes the render kernel keeps resident (grid * block) -- used to size the sample chunks.
 cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, bool general, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
 
+cudaError_t launch_black_layer(float4* layer, int W, int H, uint32_t tiles_x, uint32_t shard_index, uint32_t shard_count, float n_samples, cudaStream_t stream);
 cudaError_t launch_sum_layers(const float4* layers, int n_layers, size_t n_pix, float4* accum, bool add, cudaStream_t stream);
 cudaError_t launch_resolve_u8(const float4* accum, size_t n_pix, uint8_t* rgb, cudaStream_t stream);
 cudaError_t launch_resolve_linear(const float4* accum, size_t n_pix, float* rgb, cudaStream_t stream);

@@ -167,7 +167,6 @@ def test_primary_hit_parity(gpu_rt, oracle, name, W, H, step):
     sc = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 1)
     xy, rays = _centre_rays(osc, W, H, step)
     ref = osc.trace_primary(rays, want_second=False)
-    margin_all = np.minimum(np.minimum(ref["u"], ref["v"]), 1 - ref["u"] - ref["v"])
     for precision in (32, 64):
         tid, t = sc.trace_primary(rays, precision=precision)
         same = tid == ref["tri_id"]
@@ -176,33 +175,37 @@ def test_primary_hit_parity(gpu_rt, oracle, name, W, H, step):
         tol = 1e-5 if precision == 32 else 1e-12
         assert rel.max() <= tol, (precision, float(rel.max()))
         assert np.isinf(t[same & (ref["tri_id"] < 0)]).all()
-        # rays that are nowhere near an edge of the oracle's hit must agree without exception
-        interior = (ref["tri_id"] >= 0) & (margin_all > (1e-5 if precision == 64 else 2e-3))
         bad = np.nonzero(~same)[0]
-        n_tie = 0
+        n_tie = n_one_sided = 0
         if bad.size:
-            # every mismatch must be a tie: the oracle's hit sits on an edge (margin <= 1e-5) or a second triangle lies
-            # within 1e-5 * t (second_t is brute force over all triangles, so only evaluated for the mismatches), or the
-            # oracle itself missed (silhouette).  Pixel-centre rays of these symmetric scenes DO land exactly on shared
-            # edges (image diagonals = wall corners, quad diagonals), so ties are not rare: ~0.1 % of the rays.
+            # SURVEY.md 8d, strictly: EVERY id mismatch must be a tie -- the oracle's hit sits on an edge (barycentric margin <= 1e-5)
+            # or another triangle lies within 1e-5 t of it (second_t: brute force over all triangles, evaluated for the mismatches
+            # only).  Pixel-centre rays of these symmetric scenes DO land exactly on shared edges (image diagonals = wall corners,
+            # quad diagonals), so ties are not rare: ~0.1 % of the rays.  FP32 and f64 are held to the SAME rule.
             sub = osc.trace_primary(rays[bad], want_second=True)
             margin = np.minimum(np.minimum(sub["u"], sub["v"]), 1 - sub["u"] - sub["v"])
             gap = np.abs(sub["second_t"] - sub["t"])
-            is_tie = (margin <= 1e-5) | (gap <= 1e-5 * np.abs(sub["t"])) | (sub["tri_id"] < 0)
+            both = (sub["tri_id"] >= 0) & (tid[bad] >= 0)
+            is_tie = both & ((margin <= 1e-5) | (gap <= 1e-5 * np.abs(sub["t"])))
             n_tie = int(is_tie.sum())
-            if precision == 64:
-                assert is_tie.all(), (name, bad[~is_tie][:10])
-            else:
-                # FP32 production traversal: the barycentrics of a small far triangle carry ~eps*distance/size of error,
-                # so near-edge rays (margin <= 2e-3) may pick the neighbouring triangle; nothing else may differ, and a
-                # mismatch may not be a LEAK (hit reported far behind the oracle's surface) except at exact ties
-                near_edge = is_tie | (margin <= 2e-3)
-                assert near_edge.all(), (name, bad[~near_edge][:10], margin[~near_edge][:10])
-                leak = ~is_tie & ((tid[bad] < 0) | (np.abs(t[bad] - sub["t"]) > 1e-3 * sub["t"]))
-                assert leak.sum() <= 2e-4 * rays.shape[0], (name, int(leak.sum()))
-        assert same[interior].all()
-        assert same.mean() >= 0.995, (precision, float(same.mean()))
-        print(f"{name} {W}x{H} fp{precision}: id match {same.mean():.6f}, mismatches {bad.size} (ties {n_tie}), max rel t err {rel.max():.2e}")
+            assert (is_tie | ~both).all(), (name, precision, bad[both & ~is_tie][:10], margin[both & ~is_tie][:10])
+            # one side hits, the other misses (silhouettes; the +2e-6 barycentric overlap of the FP32 tri_test): NOT a tie -- counted
+            # separately and bounded: at most 1e-4 of the rays (ids equal on >= 99.99 %), and the hit that exists must be within 1e-4 of an edge
+            one_sided = ~both
+            n_one_sided = int(one_sided.sum())
+            assert n_one_sided <= max(1, int(1e-4 * rays.shape[0])), (name, precision, n_one_sided)
+            gpu_only = one_sided & (tid[bad] >= 0)
+            oracle_only = one_sided & (sub["tri_id"] >= 0)
+            assert (margin[oracle_only] <= 1e-4).all()
+            if gpu_only.any():                                         # the GPU's extra hit: within 1e-4 of an edge of that triangle (oracle barycentrics of the same ray)
+                for k in np.nonzero(gpu_only)[0]:
+                    tri = fl.tri_v[tid[bad][k]].reshape(3, 3)
+                    o, d = rays[bad][k, :3], rays[bad][k, 3:]
+                    e1, e2 = tri[1] - tri[0], tri[2] - tri[0]
+                    M = np.stack([e1, e2, -d], axis=1)
+                    uvt = np.linalg.solve(M, o - tri[0])
+                    assert min(uvt[0], uvt[1], 1 - uvt[0] - uvt[1]) >= -1e-4, (name, k, uvt)
+        print(f"{name} {W}x{H} fp{precision}: id match {same.mean():.6f}, mismatches {bad.size} (ties {n_tie}, one-sided {n_one_sided}), max rel t err {rel.max():.2e}")
     # the device's own FP32 camera rays agree with the oracle's f64 rays (rendering.rs:71-84)
     dev_rays = sc.primary_rays(xy[:4096], np.full((min(4096, xy.shape[0]), 2), 0.5))
     assert np.allclose(dev_rays, rays[:4096], atol=2e-6)
@@ -263,6 +266,131 @@ def test_image_statistics_per_pixel_zscores(gpu_rt):
     z = z[np.isfinite(z)]
     assert abs(np.median(z)) < 0.15 and abs(z.mean()) < 0.25, (np.median(z), z.mean())
     assert np.quantile(np.abs(z), 0.9) < 3.0
+    sc.close()
+
+
+def test_converged_frame_256x144_and_rgb8_criterion(gpu_rt, oracle):
+    """VERDICT r1 item 2 / SURVEY.md 8d: practice7_4 at 256x144 (the 16:9 stretch of the north-star frame), 4 096 spp on both sides:
+    (a) the linear-radiance gates of test_converged_image_parity on 147 456 pixels (16x9 grid of blocks), (b) on the RGB8 OUTPUT
+    (rt_render bytes vs the oracle's color_to_pixel bytes) RMSE <= 2/255, mean signed error ~ 0."""
+    name, W, H, spp = "practice7_4", 256, 144, 4096
+    g = np.load(os.path.join(GOLDEN, f"converged_{name}_{W}x{H}_{spp}.npz"))
+    ref, var, rgb_ref = g["mean"].astype(np.float64), g["var"].astype(np.float64), g["rgb"]
+    sc = gpu_rt.Scene.from_gltf(scene_path(name), W, H, spp)
+    img, st = sc.render_linear(seed=2024, collect_stats=True)
+    img = img.astype(np.float64)
+    assert st["samples"] == W * H * spp and st["attempt_cap_hits"] <= 1e-6 * st["samples"] and st["nonfinite_samples"] <= 1e-6 * st["samples"]
+    lg, lr = _lum(img), _lum(ref)
+    assert abs(lg.mean() - lr.mean()) / lr.mean() <= 0.005, (lg.mean(), lr.mean())
+    lvar = _lum(var) * (2.0 / spp)
+    for j in range(9):
+        for i in range(16):
+            sl = (slice(j * 16, (j + 1) * 16), slice(i * 16, (i + 1) * 16))
+            diff = abs(lg[sl].mean() - lr[sl].mean())
+            sigma = np.sqrt(lvar[sl].sum()) / lg[sl].size
+            assert diff <= max(0.02 * lr[sl].mean(), 4.5 * sigma), (j, i, diff, lr[sl].mean(), sigma)
+    rmse, floor = np.sqrt(np.mean((img - ref) ** 2)), np.sqrt(np.mean(var * (2.0 / spp)))
+    assert rmse <= 1.5 * floor, (rmse, floor)
+    # per-pixel differences are centred.  Two independent renders of the same estimator at the same spp have a SYMMETRIC difference
+    # whatever the per-pixel distribution: the median is 0 and GPU > oracle on half of the pixels (sign test, 4 sigma).  (The mean of
+    # z-scores built from the ORACLE's variance estimate is not symmetric: a pixel whose rare bright sample the oracle has not seen
+    # gets a small sigma, so it is not used as a gate.)
+    z = (lg - lr) / np.sqrt(lvar + 1e-12)
+    assert abs(np.median(z)) < 0.05, float(np.median(z))
+    nz = lg != lr
+    assert abs((lg > lr)[nz].mean() - 0.5) < 4 * 0.5 / np.sqrt(nz.sum()), float((lg > lr)[nz].mean())
+    # RGB8 output at this sample count: the difference to the oracle's bytes must be pure Monte-Carlo noise, i.e. no larger than the
+    # difference between two independent ORACLE renders (seed 0 vs seed 1, committed as rgb / rgb2).  Measured: ~9/255 -- SURVEY.md
+    # 8d's "RMSE <= 2/255 at >= 4 096 spp" is not reachable at 4 096 spp by ANY renderer of this estimator, the reference included;
+    # test_rgb8_criterion below meets the 2/255 figure at the sample count it really needs.
+    u8, _ = sc.render(seed=2024)
+    d8 = u8.astype(np.float64) - rgb_ref.astype(np.float64)
+    floor8 = np.sqrt(np.mean((g["rgb2"].astype(np.float64) - rgb_ref.astype(np.float64)) ** 2))
+    rmse8 = np.sqrt(np.mean(d8 ** 2))
+    assert rmse8 <= 1.15 * floor8, (rmse8, floor8)
+    assert abs(d8.mean()) < 0.1, d8.mean()
+    print(f"256x144x4096: linear rmse {rmse:.5f} (floor {floor:.5f}), RGB8 rmse {rmse8:.3f}/255 (oracle vs oracle {floor8:.3f}/255), mean signed {d8.mean():+.4f}/255")
+    sc.close()
+
+
+def test_rgb8_criterion(gpu_rt):
+    """SURVEY.md 8d parity rule 2, last clause: "on the RGB8 output, RMSE <= 2/255 at >= 4 096 spp".  Two independent 4 096-spp renders
+    of practice7_4 differ by ~9/255 (previous test), so the figure needs ~20x more samples per side: the committed oracle render of the
+    16:9 frame at 64x36 with 131 072 spp against rt_render at 524 288 spp (1.2e9 camera paths, well under a second of B200 time)."""
+    name, W, H, ospp, gspp = "practice7_4", 64, 36, 131072, 524288
+    g = np.load(os.path.join(GOLDEN, f"converged_{name}_{W}x{H}_{ospp}.npz"))
+    sc = gpu_rt.Scene.from_gltf(scene_path(name), W, H, gspp)
+    u8, st = sc.render(seed=77, collect_stats=True)
+    assert st["samples"] == W * H * gspp and st["attempt_cap_hits"] <= 1e-6 * st["samples"] and st["nonfinite_samples"] <= 1e-6 * st["samples"]
+    d8 = u8.astype(np.float64) - g["rgb"].astype(np.float64)
+    rmse8 = np.sqrt(np.mean(d8 ** 2))
+    assert rmse8 <= 2.0, rmse8
+    assert abs(d8.mean()) < 0.15, d8.mean()
+    lin, _ = sc.render_linear(seed=77)
+    ref = g["mean"].astype(np.float64)
+    lg, lr = _lum(lin.astype(np.float64)), _lum(ref)
+    assert abs(lg.mean() - lr.mean()) / lr.mean() < 0.002, (lg.mean(), lr.mean())
+    print(f"64x36: GPU {gspp} spp vs oracle {ospp} spp: RGB8 rmse {rmse8:.3f}/255, mean signed {d8.mean():+.4f}/255, max |d| {np.abs(d8).max():.0f}")
+    sc.close()
+
+
+def _log_polar_directions(axis, n, rng, theta_min=1e-6):
+    """Directions around `axis` with the polar angle log-uniform in [theta_min, pi]: an importance-sampled integrator that
+    resolves a lobe of any width.  Returns (l, 1/q) with q the density per solid angle."""
+    a = axis / np.linalg.norm(axis)
+    t1 = np.cross(a, [0.0, 1.0, 0.0] if abs(a[1]) < 0.9 else [1.0, 0.0, 0.0]); t1 /= np.linalg.norm(t1)
+    t2 = np.cross(a, t1)
+    L = np.log(np.pi / theta_min)
+    th = theta_min * np.exp(rng.random(n) * L)
+    ph = rng.random(n) * 2 * np.pi
+    l = np.cos(th)[:, None] * a + np.sin(th)[:, None] * (np.cos(ph)[:, None] * t1 + np.sin(ph)[:, None] * t2)
+    inv_q = th * L * 2 * np.pi * np.sin(th)
+    return l, inv_q
+
+
+@pytest.mark.parametrize("rough", [0.03, 0.2, 0.5, 1.0])
+def test_device_pdf_normalisation(gpu_rt, rough):
+    """Methodology of the reference's own test (tests.rs:22-49: integral of the pdf over the sphere = 1), two-sided, fixed seed, with
+    an importance-sampled integrator so that the alpha = 9e-4 lobe of roughness 0.03 is resolved, for each DEVICE pdf:
+    cosine (distributions.rs:65-67), VNDF (:276-297; over half vectors above the horizon -- the reference's formula also gives mass to
+    half vectors below it, which its sampler never draws, :232), lights (:160-184) and the mixture (:194-201)."""
+    rng = np.random.default_rng(31)
+    n = np.array([0.0, 0.0, 1.0]); v = np.array([0.6, 0.0, 0.8])
+    cnt = 1_000_000
+    mirror = 2 * n.dot(v) * n - v
+    l, inv_q = _log_polar_directions(mirror, cnt, rng)
+    l32 = np.ascontiguousarray(l, dtype=np.float32)
+    l64 = l32.astype(np.float64); l64 /= np.linalg.norm(l64, axis=1, keepdims=True)
+    N = np.tile(n.astype(np.float32), (cnt, 1)); V = np.tile(v.astype(np.float32), (cnt, 1)); R = np.full((cnt, 1), rough, dtype=np.float32)
+    pv = gpu_rt.eval_fn(gpu_rt.FN_PDF_VNDF, np.concatenate([N, l32, V, R], axis=1))[:, 0].astype(np.float64)
+    above = ((l64 + v) @ n) > 0
+    w = np.where(above & np.isfinite(pv), pv, 0.0) * inv_q
+    est, err = w.mean(), w.std() / np.sqrt(cnt)
+    assert abs(est - 1.0) < max(5 * err, 0.01), ("vndf", rough, est, err)
+    pc = gpu_rt.eval_fn(gpu_rt.FN_PDF_COSINE, np.concatenate([N, l32], axis=1))[:, 0].astype(np.float64)
+    wc = pc * inv_q
+    assert abs(wc.mean() - 1.0) < max(5 * wc.std() / np.sqrt(cnt), 0.01), ("cosine", wc.mean())
+    # lights + mixture on practice7_4 from a point on the floor (two triangle lights in the ceiling corners)
+    sc = gpu_rt.Scene.from_gltf(scene_path("practice7_4"), 16, 16, 1)
+    P = np.tile(np.array([[0.3, -1.99, 0.2]], dtype=np.float32), (cnt, 1))
+    up = np.array([0.0, 1.0, 0.0])
+    vv = np.array([0.0, 0.8, 0.6])
+    lu = rng.normal(size=(cnt, 3)); lu /= np.linalg.norm(lu, axis=1, keepdims=True)
+    lu32 = np.ascontiguousarray(lu, dtype=np.float32)
+    pl = sc.eval(gpu_rt.FN_PDF_LIGHT, np.concatenate([P, lu32], axis=1))[:, 0].astype(np.float64) * 4 * np.pi
+    assert abs(pl.mean() - 1.0) < max(5 * pl.std() / np.sqrt(cnt), 0.01), ("light", pl.mean())
+    # mixture = mean of the three (one-sample MIS, uniform component choice): integrate with the log-polar proposal around the mirror
+    # direction for the VNDF part and uniformly for the rest -- two estimates of two different integrals, both must be right:
+    #   uniform directions resolve cosine + lights (the VNDF lobe adds its share only for rough surfaces)
+    if rough >= 0.2:
+        Nn = np.tile(up.astype(np.float32), (cnt, 1)); Vv = np.tile(vv.astype(np.float32), (cnt, 1))
+        pm = sc.eval(gpu_rt.FN_PDF_MIX, np.concatenate([P, Nn, lu32, Vv, R], axis=1))[:, 0].astype(np.float64) * 4 * np.pi
+        pvu = gpu_rt.eval_fn(gpu_rt.FN_PDF_VNDF, np.concatenate([Nn, lu32, Vv, R], axis=1))[:, 0].astype(np.float64) * 4 * np.pi
+        pcu = gpu_rt.eval_fn(gpu_rt.FN_PDF_COSINE, np.concatenate([Nn, lu32], axis=1))[:, 0].astype(np.float64) * 4 * np.pi
+        assert np.allclose(pm, (pvu + pcu + pl) / 3.0, rtol=2e-3, atol=1e-6)
+        above_u = ((lu + vv) @ up) > 0
+        tot = np.where(above_u, pvu, 0.0) / 3 + pcu / 3 + pl / 3
+        assert abs(tot.mean() - 1.0) < max(5 * tot.std() / np.sqrt(cnt), 0.02), ("mix", rough, tot.mean())
     sc.close()
 
 
@@ -350,6 +478,34 @@ def test_error_codes_on_gpu(gpu_rt):
     lin, _ = e0.render_linear()
     assert np.allclose(lin, [0.25, 0.5, 1.0])
     e0.close()
+
+
+def test_ray_depth_zero_is_black_and_bad_depth_is_rejected(gpu_rt, oracle):
+    """rendering.rs:93-95: recursion_depth <= 0 returns black before the scene is looked at -- also for the camera ray; a negative
+    depth is an error here, not a wrapped bit field."""
+    fl = oracle.convert_gltf_to_scene(scene_path("practice7_1"), 24, 16, 4)
+    fl.bg_color = np.array([0.3, 0.3, 0.3])
+    for kv in (0, 10):
+        sc = gpu_rt.Scene.from_flat(fl, ray_depth=0)
+        lin, st = sc.render_linear(kernel_variant=kv)
+        assert not lin.any() and st["samples"] == 24 * 16 * 4
+        u8, _ = sc.render(kernel_variant=kv)
+        assert not u8.any()
+        sc.close()
+    fl.ray_depth = 0
+    assert not oracle.OracleScene(fl).render()["mean"].any()              # the oracle agrees
+    sc = gpu_rt.Scene.from_flat(fl, ray_depth=-1)
+    with pytest.raises(gpu_rt.RtError) as e:
+        sc.render()
+    assert e.value.code == gpu_rt.RT_ERR_INVALID
+    sc.close()
+    # max_attempts above the 7-bit attempt counter is clamped to 127 for every kernel: both kernels still render the same image
+    sc = gpu_rt.Scene.from_gltf(scene_path("practice7_1"), 32, 32, 64)
+    a, _ = sc.render_linear(seed=3, kernel_variant=10, max_attempts=1000)
+    b, _ = sc.render_linear(seed=3, kernel_variant=30, max_attempts=1000)
+    d = np.abs(a.astype(np.float64) - b)
+    assert np.median(d) <= 1e-5 * np.abs(a).mean()
+    sc.close()
 
 
 def test_many_lights_use_the_light_bvh(gpu_rt, oracle):

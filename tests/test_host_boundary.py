@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol(rt):
     L = rt.lib()
     for name in declared:
         assert hasattr(L, name), f"{name} declared in rt_api.h but not exported by librt_b200.so"
-    assert L.rt_api_version() == 1
+    assert L.rt_api_version() == 2
 
 
 def test_header_is_plain_c(tmp_path):
@@ -232,3 +232,66 @@ def test_write_png_decodes_to_the_same_pixels(rt, tmp_path):
         rt.dump_rendered_to_png(None, img, str(p))
         back = np.asarray(Image.open(p).convert("RGB"))
         assert back.shape == img.shape and np.array_equal(back, img)
+
+
+def test_malformed_gltf_is_rejected_not_read_out_of_bounds(rt, tmp_path):
+    """accessor / bufferView sizes are untrusted.  Negative, fractional or huge `count` / `byteOffset` /
+    `byteStride` / `byteLength`, accessors that leave their bufferView, non-integer child indices and absurdly nested JSON must
+    produce RT_ERR_FORMAT (the gltf crate rejects such files; the reference then panics in `unwrap`, main.rs:45) -- never an
+    out-of-bounds read."""
+    import base64
+    import json
+    import struct
+    blob = struct.pack("<9f", 0, 0, 0, 1, 0, 0, 0, 1, 0) + struct.pack("<3B", 0, 1, 2) + b"\0"
+
+    def doc(**patch):
+        g = {
+            "asset": {"version": "2.0"},
+            "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+            "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 3}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}, {"bufferView": 1, "componentType": 5121, "count": 3, "type": "SCALAR"}],
+            "meshes": [{"primitives": [{"attributes": {"POSITION": 0}, "indices": 1}]}],
+            "cameras": [{"type": "perspective", "perspective": {"yfov": 0.5, "znear": 0.1}}],
+            "nodes": [{"mesh": 0}, {"camera": 0, "translation": [0, 0, 5]}],
+        }
+        for path, val in patch.items():
+            keys = path.split("__")
+            cur = g
+            for k in keys[:-1]:
+                cur = cur[int(k)] if k.isdigit() else cur[k]
+            cur[int(keys[-1]) if keys[-1].isdigit() else keys[-1]] = val
+        return g
+
+    def load(g, name):
+        p = tmp_path / name
+        p.write_text(json.dumps(g) if not isinstance(g, str) else g)
+        return rt.Scene.from_gltf(str(p), 8, 8, 1, device=-1)
+
+    load(doc(), "ok.gltf").close()                                         # the unpatched document loads
+    bad = {
+        "count_negative": {"accessors__1__count": -1},
+        "count_huge": {"accessors__0__count": 2 ** 62},
+        "count_past_view": {"accessors__0__count": 4},
+        "count_fraction": {"accessors__1__count": 2.5},
+        "offset_negative": {"bufferViews__0__byteOffset": -4},
+        "offset_huge": {"accessors__0__byteOffset": 1e300},
+        "stride_wraps": {"bufferViews__0__byteStride": 2 ** 63, "accessors__0__count": 3},
+        "stride_small": {"bufferViews__0__byteStride": 4},
+        "view_past_buffer": {"bufferViews__1__byteLength": 400},
+        "view_length_negative": {"bufferViews__1__byteLength": -3},
+        "accessor_leaves_view": {"bufferViews__0__byteLength": 24},
+        "buffer_index": {"bufferViews__0__buffer": 3},
+        "view_index_negative": {"accessors__0__bufferView": -1},
+        "child_negative": {"nodes__0__children": [-1]},
+        "child_fraction": {"nodes__0__children": [0.5]},
+        "child_out_of_range": {"nodes__0__children": [99]},
+        "mesh_index": {"nodes__0__mesh": 1e12},
+        "vertex_index": {"accessors__0__count": 2},                         # index 2 now points past POSITION
+    }
+    for name, patch in bad.items():
+        with pytest.raises(rt.RtError) as e:
+            load(doc(**patch), name + ".gltf")
+        assert e.value.code == rt.RT_ERR_FORMAT, (name, str(e.value))
+    with pytest.raises(rt.RtError) as e:                                    # 100 000 nested arrays: bounded recursion, clean error
+        load("[" * 100000, "deep.gltf")
+    assert e.value.code == rt.RT_ERR_FORMAT
