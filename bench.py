@@ -15,8 +15,11 @@ Keys of the JSON line (rank 0):
                H2D scene upload) + render + (reduce) + resolve + D2H of the W*H*3 result, every step
   roofline     FP32-issue roofline of the render kernel (the scene is ~21 KB and shared-memory
                resident, so HBM is not the bound): achieved = algorithmic flop/sample (fixed constants x counts
-               measured by the kernel's own stats mode) x samples / kernel time; peak = FFMA micro-benchmark run
-               in this process ("measured here"); hbm_* = the secondary HBM figures
+               measured by the kernel's own stats mode on the TIMED frame shape, 16 spp) x samples / kernel time;
+               peak = FFMA micro-benchmark run in this process ("measured here"); hbm_* = the secondary HBM figures
+               from the launch's actual chunk count; traffic = ncu DRAM bytes of this launch when profiles/ holds a
+               capture of THIS build (hash of the kernel sources), else null
+  phases       per-frame device time of render (path tracing + layer sum) / reduce / resolve, max and min over ranks
   cpu_baseline the oracle (f64 CPU restatement of the reference; the Rust binary cannot be built here) on a
                bounded sample of the same workload on this box's host cores
 `--impl reference` times that CPU restatement as its own arm (rank 0 only)."""
@@ -32,6 +35,20 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
 SCENE = "practice7_4"
+TRAFFIC_FILE = "r2_bench_traffic.json"
+KERNEL_SOURCES = ("rt_render_wave.cuh", "rt_device.cuh", "rt_kernels.cu", "rt_kernels.h")
+
+
+def kernel_source_sha16():
+    """Identity of the render kernel's build: sha256 over the kernel sources.  An ncu capture under profiles/ is quoted as
+    `roofline.traffic` only when it was taken from exactly these sources (tools/ncu_traffic.py stores the same hash)."""
+    import hashlib
+    h = hashlib.sha256()
+    for f in KERNEL_SOURCES:
+        h.update(open(os.path.join(ROOT, "raytracing-course-2024_b200", "csrc", f), "rb").read())
+    return h.hexdigest()[:16]
+
+
 C_NODE, C_TRI, C_ATTEMPT, C_SHADE = 20.0, 50.0, 260.0, 120.0        # flop constants of SURVEY.md 8d
 
 
@@ -203,20 +220,27 @@ def main():
         rt.resolve_device(acc_ptr, W, H, rgb_ptr, s)
 
     ev_pairs = []
+    n_chunks_seen = []
 
     def step(record=False):
+        ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
+        if record:
+            ev[0].record(stream)
         accum.zero_()
         if record:
-            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            e0.record(stream)
+            ev[1].record(stream)
         if hi > lo:
             scene.render_accumulate_device(accum.data_ptr(), sp, seed=args.seed, sample_begin=lo, sample_end=hi, kernel_variant=args.variant)
         if record:
-            e1.record(stream)
-            ev_pairs.append((e0, e1))
+            ev[2].record(stream)
         multigpu.reduce_to_root(accum, 0)
+        if record:
+            ev[3].record(stream)
         if rank == 0:
             resolve(accum.data_ptr(), rgb_dev.data_ptr(), sp)
+        if record:
+            ev[4].record(stream)
+            ev_pairs.append(ev)
 
     def barrier():
         if world > 1:
@@ -235,11 +259,15 @@ def main():
     flop_per_sample = None
     counts = None
     if rank == 0:
-        sw, sh = max(64, W // 8), max(36, H // 8)
-        scene.set_frame(sw, sh, 64)
-        _, st = scene.render_linear(seed=args.seed, collect_stats=True)
-        _, kcfg = scene.render(seed=args.seed, kernel_variant=args.variant)                 # the timed build's launch configuration
+        # counters of the TIMED frame shape (same pixels, same camera), 16 spp through the instrumented build: ~50 ms of kernel time
+        scene.set_frame(W, H, min(16, S))
+        stats_acc = torch.zeros(H * W * 4, dtype=torch.float32, device=dev)
+        st = scene.render_accumulate_device(stats_acc.data_ptr(), sp, want_stats=True, seed=args.seed, collect_stats=True, kernel_variant=args.variant)
+        del stats_acc
         scene.set_frame(W, H, S)
+        kcfg = scene.render_accumulate_device(accum.data_ptr(), sp, want_stats=True, seed=args.seed, sample_begin=lo, sample_end=min(hi, lo + 8),
+                                              kernel_variant=args.variant)                  # the timed build's launch configuration (8 samples)
+
         n = st["samples"]
         counts = {k: st[k] / n for k in ("segments", "vertices", "attempts", "node_tests", "tri_tests", "light_tri_tests")}
         counts["attempt_cap_hits"] = st["attempt_cap_hits"]; counts["nonfinite_samples"] = st["nonfinite_samples"]
@@ -259,7 +287,20 @@ def main():
     t_wall1 = time.time()
     clk = clocks.stop(t_wall0, t_wall1) if clocks else None
     ms_total = max_over_ranks(e_start.elapsed_time(e_end))
-    kern_ms = max_over_ranks(sum(a.elapsed_time(b) for a, b in ev_pairs) / max(1, len(ev_pairs)))
+    nst = max(1, len(ev_pairs))
+    my_phase = [sum(e[k].elapsed_time(e[k + 1]) for e in ev_pairs) / nst for k in range(4)]      # zero, render, reduce, resolve
+    kern_ms_local = my_phase[1]
+    kern_ms = max_over_ranks(kern_ms_local)
+    if world > 1:
+        gathered = [None] * world
+        dist.all_gather_object(gathered, my_phase)
+    else:
+        gathered = [my_phase]
+    phases = {name: {"max": max(g[k] for g in gathered), "min": min(g[k] for g in gathered)} for k, name in enumerate(("zero_ms", "render_ms", "reduce_ms", "resolve_ms"))}
+    phases["resolve_ms"] = {"rank0": gathered[0][3]}
+    # a rank that finishes its render early waits inside the reduce: the collective's own cost is its MIN over ranks, and
+    # (max render - min render) is the rank skew of the persistent kernel's tail
+    phases["note"] = "reduce min over ranks = the collective itself; render max - min = rank skew (absorbed by the other ranks' reduce wait)"
     total_samples = float(W) * H * S
     value = total_samples * args.steps / (ms_total * 1e-3) / 1e6
 
@@ -297,18 +338,24 @@ def main():
         assert int(rgb_host.max()) > 0, "rendered frame is black"
         frac_samples = (hi - lo) / S
         achieved = flop_per_sample * total_samples * frac_samples / (kern_ms * 1e-3) / 1e12      # this rank's kernel
-        hbm_bytes = float(W) * H * 16 * 3                                                   # layers write + sum_layers read/write
+        full = scene.render_accumulate_device(accum.data_ptr(), sp, want_stats=True, seed=args.seed, sample_begin=lo, sample_end=hi, kernel_variant=args.variant)
+        n_chunks = int(full["n_chunks"])                                                    # of the timed launch (same arguments)
+        # the render kernel writes n_chunks x W*H float4 layers (one store per (pixel, chunk)) -- its algorithmic HBM bytes; the whole
+        # step also reads them back in sum_layers and reads + writes the accumulator once
+        hbm_bytes = float(W) * H * 16 * n_chunks
+        hbm_step_bytes = float(W) * H * 16 * (2 * n_chunks + 2)
         peaks = {}
         try:
             peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
         except Exception:
             pass
-        traffic, traffic_src = None, None
+        traffic, traffic_src = None, "unmeasured for this build (no ncu capture of these kernel sources under profiles/)"
         try:                                                  # measured DRAM bytes of this exact launch (ncu, committed under profiles/)
-            tr = json.load(open(os.path.join(ROOT, "profiles", "r1_v3b_bench_traffic.json")))
-            if (W, H, S, world, args.scene) == (3840, 2160, 1024, 1, SCENE):
+            tr = json.load(open(os.path.join(ROOT, "profiles", TRAFFIC_FILE)))
+            if (W, H, S, world, args.scene) == (3840, 2160, 1024, 1, SCENE) and tr.get("kernel_source_sha16") == kernel_source_sha16():
                 traffic = tr["dram__bytes_read.sum"] + tr["dram__bytes_write.sum"]
-                traffic_src = "profiles/r1_v3b_bench_traffic.json (ncu dram__bytes_read.sum + dram__bytes_write.sum of the same launch)"
+                traffic_src = (f"profiles/{TRAFFIC_FILE}: ncu dram__bytes_read.sum + dram__bytes_write.sum of the render kernel of `{tr.get('command')}`, "
+                               f"kernel sources sha16 {tr.get('kernel_source_sha16')} = this build")
         except Exception:
             pass
         cpu = None
@@ -320,18 +367,21 @@ def main():
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
             "dtype": "f32", "data": "scene file scenes/practice7_4.gltf (fixed input, 92 triangles); no synthetic tensors",
             "config": {"workload": f"{args.scene} {W}x{H} {S} spp ray_depth 6, sample-sharded over {world} GPU(s), Philox seed {args.seed}",
-                       "l2_note": "inputs are a 21 KB scene staged in shared memory; each step rewrites the %.0f MB accumulator (> L2 is not needed: nothing is re-read across steps)" % (hbm_bytes / 3 / 1e6),
+                       "l2_note": "inputs are a 21 KB scene staged in shared memory; each step rewrites %.0f MB of radiance layers and the 133 MB accumulator (> L2 126 MB; nothing is re-read across steps)" % (hbm_bytes / 1e6),
                        "scene_in_shared_memory": bool(info["scene_in_shared_memory"]), "bvh_nodes": info["n_nodes"], "kernel_variant": args.variant},
             "e2e": {"value": e2e_value, "unit": "Msamples/s", "h2d_bytes_per_step": int(info["device_bytes"]) * world, "d2h_bytes_per_step": W * H * 3,
                     "steps": e2e_n, "ms_per_step": e2e_ms / e2e_n},
             "gpu_launches": args.steps * (2 * world + 1),
             "clocks": clk,
+            "phases": phases,
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": peak_tflops, "unit": "TFLOP/s", "frac": achieved / peak_tflops if peak_tflops else None,
                          "traffic": traffic, "traffic_source": traffic_src, "peak_source": "FFMA micro-benchmark measured in this process (MEASURED_PEAKS.json has no FP32 entry)",
                          "kernel": kernel_name(kcfg), "launch": {k: kcfg[k] for k in ("block_threads", "blocks_per_sm", "grid_blocks", "regs_per_thread", "smem_bytes_per_block")},
                          "kernel_ms": kern_ms, "flop_per_sample": flop_per_sample, "per_sample": counts,
+                         "per_sample_source": f"stats build on the timed frame shape {W}x{H} at {min(16, S)} spp", "n_chunks": n_chunks,
+                         "kernel_source_sha16": kernel_source_sha16(),
                          "flop_constants": {"node": C_NODE, "tri": C_TRI, "attempt": C_ATTEMPT, "shade": C_SHADE},
-                         "hbm_algorithmic_bytes": hbm_bytes, "hbm_achieved_gbs": hbm_bytes / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
+                         "hbm_algorithmic_bytes": hbm_bytes, "hbm_step_bytes": hbm_step_bytes, "hbm_achieved_gbs": hbm_bytes / (kern_ms * 1e-3) / 1e9, "hbm_peak_gbs": peaks.get("hbm_gbs"),
                          "hbm_frac": (hbm_bytes / (kern_ms * 1e-3) / 1e9) / peaks["hbm_gbs"] if peaks.get("hbm_gbs") else None,
                          "mrays_per_s": counts["segments"] * total_samples * frac_samples / (kern_ms * 1e-3) / 1e6,
                          # the resource ncu shows closest to saturation (profiles/): the shared-memory data pipe.  Algorithmic bytes per

@@ -122,7 +122,7 @@ typedef struct RtStats {
     int32_t  kernel;                  /* render kernel that ran: 1 = per-lane megakernel, 2 / 3 = warp-local wavefront (while-while / phased bursts) */
     int32_t  block_threads, blocks_per_sm, grid_blocks, regs_per_thread, smem_bytes_per_block;   /* its launch configuration */
     int32_t  scene_in_shared_memory;  /* 1: the scene blob was staged in shared memory by every block      */
-    int32_t  reserved2;
+    int32_t  n_chunks;                /* per-chunk float4 layers the render kernel wrote (summed by sum_layers in fixed order)      */
     double   render_ms;               /* device time of the path-tracing kernel + layer sum (slowest device for rt_render_multi) */
     double   reduce_ms;               /* device time of the cross-GPU framebuffer reduce (0 on one GPU)    */
     double   resolve_ms;              /* device time of color_to_pixel                                     */
@@ -155,6 +155,10 @@ int rt_scene_create(const RtSceneDesc* desc, int32_t device, RtScene** out);
  * Null extension arrays mean: all triangles / zero positions / identity rotations / ior 1 / RT_MATERIAL_PBR. */
 int rt_scene_create2(const RtSceneDesc2* desc, int32_t device, RtScene** out);
 void rt_scene_destroy(RtScene* scene);
+/* rt_scene_destroy parks the scene's big frame buffers (per-chunk radiance layers, accumulator, result bytes) in a small process-wide
+ * cache so that the next scene on the same device does not pay cudaMalloc + cudaFree of ~0.7 GB per frame (at most 8 blocks are
+ * kept).  This call frees them all. */
+int rt_release_device_cache(void);
 /* Host-side view of the flat scene (pointers stay valid until rt_scene_destroy) -- what the loader produced. */
 int rt_scene_get_desc(const RtScene* scene, RtSceneDesc* out);
 int rt_scene_get_desc2(const RtScene* scene, RtSceneDesc2* out);   /* extension arrays are null for a triangles-only scene */

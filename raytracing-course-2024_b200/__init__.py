@@ -73,7 +73,7 @@ class RtStats(C.Structure):
     _fields_ = [(k, C.c_uint64) for k in ("samples", "segments", "vertices", "attempts", "node_tests", "tri_tests", "light_tri_tests",
                                           "attempt_cap_hits", "nonfinite_samples", "kernel_launches")] + [("kernel_ms", C.c_double), ("total_ms", C.c_double)] + \
                [(k, C.c_int32) for k in ("kernel", "block_threads", "blocks_per_sm", "grid_blocks", "regs_per_thread", "smem_bytes_per_block",
-                                         "scene_in_shared_memory", "reserved2")] + [("render_ms", C.c_double), ("reduce_ms", C.c_double), ("resolve_ms", C.c_double)]
+                                         "scene_in_shared_memory", "n_chunks")] + [("render_ms", C.c_double), ("reduce_ms", C.c_double), ("resolve_ms", C.c_double)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_}
@@ -136,6 +136,11 @@ def lib():
 def _check(rc):
     if rc != RT_OK:
         raise RtError(rc, lib().rt_last_error().decode("utf-8", "replace"))
+
+
+def release_device_cache():
+    """Frees the frame buffers rt_scene_destroy parked for reuse (include/rt_api.h)."""
+    _check(lib().rt_release_device_cache())
 
 
 def device_count() -> int:

@@ -65,6 +65,7 @@ struct RtScene {
     uint8_t* rgb_dev = nullptr; size_t rgb_cap = 0;
     float* lin_dev = nullptr; size_t lin_cap = 0;
     unsigned int* work_counter = nullptr;
+    int32_t* chunk_table = nullptr;        // chunk schedule of the current launch (RenderArgs::chunk_begin)
     unsigned long long* stats_dev = nullptr;
     cudaStream_t stream = nullptr;
     cudaEvent_t ev[5] = {nullptr, nullptr, nullptr, nullptr, nullptr};
@@ -122,8 +123,10 @@ float plane_with_payload(float v, uint32_t payload, bool lower) {
 }
 bool refs_packable(const rtb::FlatBvh& b) { return b.n_nodes < 32768 && b.tri_order.size() < 4096; }
 
-std::vector<float> octant_nodes(const rtb::FlatBvh& b) {
-    const size_t wpn = RT_NODE_BYTES / 4;
+// stride_bytes: RT_NODE_BYTES (112).  Inner children are stored as BYTE offsets, so global-memory walks accept any stride; padding
+// the nodes to one 128-byte line each was tried for the large meshes and lost 10 % (more L1 footprint, power-of-two set conflicts).
+std::vector<float> octant_nodes(const rtb::FlatBvh& b, size_t stride_bytes) {
+    const size_t wpn = stride_bytes / 4;
     std::vector<float> out((size_t)std::max(b.n_nodes, 1) * wpn, 0.f);
     for (int n = 0; n < b.n_nodes; ++n) {
         const float* A = &b.box_a[(size_t)n * 4]; const float* B = &b.box_b[(size_t)n * 4]; const float* C = &b.box_c[(size_t)n * 4];
@@ -144,7 +147,7 @@ std::vector<float> octant_nodes(const rtb::FlatBvh& b) {
         }
         for (int c = 0; c < 2; ++c) {      // inner children as byte offsets (index * RT_NODE_BYTES), leaf codes unchanged
             const int32_t r = b.child[(size_t)n * 2 + (size_t)c];
-            o[24 + c] = i2f(r >= 0 ? r * (int32_t)RT_NODE_BYTES : r);
+            o[24 + c] = i2f(r >= 0 ? r * (int32_t)stride_bytes : r);
         }
     }
     return out;
@@ -362,7 +365,8 @@ int flatten_scene(RtScene* s) {
     BlobWriter w{s->blob_host};
     rtd::SceneLayout& L = s->L;
     std::memset(&L, 0, sizeof(L));
-    const std::vector<float> nodes = octant_nodes(s->bvh);
+    const size_t node_stride = RT_NODE_BYTES;      // (128-byte nodes for global-memory scenes were measured: -10 %)
+    const std::vector<float> nodes = octant_nodes(s->bvh, node_stride);
     L.nodes = w.add(nodes.data(), nodes.size() * 4);
     L.tri_t = w.add(tri_t.data(), tri_t.size() * 4);
     if (gen) L.prims = w.add(prims.data(), prims.size() * 4);
@@ -382,10 +386,10 @@ int flatten_scene(RtScene* s) {
     L.lt_t = w.add(lt_t.data(), lt_t.size() * 4);
     if (gen) L.lt_g = w.add(lt_g.data(), lt_g.size() * 4);
     if (use_light_bvh) {
-        const std::vector<float> lnodes = octant_nodes(s->light_bvh);
+        const std::vector<float> lnodes = octant_nodes(s->light_bvh, RT_NODE_BYTES);
         L.lnodes = w.add(lnodes.data(), lnodes.size() * 4);
     }
-    if (s->blob_host.size() > 0xffffffffull || (uint64_t)std::max(s->bvh.n_nodes, s->light_bvh.n_nodes) * RT_NODE_BYTES > 0x7fffffffull)
+    if (s->blob_host.size() > 0xffffffffull || (uint64_t)std::max(s->bvh.n_nodes, s->light_bvh.n_nodes) * 128u > 0x7fffffffull)
         return fail(RT_ERR_LIMIT, "scene exceeds the 4 GiB device blob / 2 GiB node array addressed by 32-bit offsets");
     L.total_bytes = (uint32_t)s->blob_host.size();
     L.n_nodes = s->bvh.n_nodes; L.n_tris = n; L.n_mats = s->n_mats; L.n_lights = n_lights;
@@ -438,12 +442,62 @@ int finish_create(RtScene* s, RtScene** out) {
     return RT_OK;
 }
 
+// Process-wide cache of the big frame buffers (per-chunk layers, accumulator, result bytes).  A host that renders one scene after
+// another (create -> render -> destroy per frame, like bench.py's end-to-end leg or a render service) would otherwise pay a
+// cudaMalloc and a cudaFree of ~0.7 GB per frame; cudaFree of such blocks was measured at 10 ms .. 0.9 s on B200.  rt_scene_destroy
+// parks the buffers here, the next scene on the same device picks them up.  At most kCacheSlots blocks per process are kept (the
+// smallest is released first); rt_release_device_cache() frees them all.
+struct CachedBlock { int device; void* p; size_t bytes; };
+const size_t kCacheSlots = 8, kCacheMinBytes = 1u << 20;
+std::mutex& cache_mutex() { static std::mutex m; return m; }
+std::vector<CachedBlock>& cache_blocks() { static std::vector<CachedBlock> v; return v; }
+
+void cache_put(void* p, size_t bytes) {
+    if (!p) return;
+    int dev = 0;
+    if (bytes < kCacheMinBytes || cudaGetDevice(&dev) != cudaSuccess) { cudaFree(p); return; }
+    void* evict = nullptr;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex());
+        std::vector<CachedBlock>& c = cache_blocks();
+        c.push_back({dev, p, bytes});
+        if (c.size() > kCacheSlots) {
+            size_t k = 0;
+            for (size_t i = 1; i < c.size(); ++i) if (c[i].bytes < c[k].bytes) k = i;
+            if (c[k].device == dev) { evict = c[k].p; c.erase(c.begin() + (long)k); }     // (another device's block stays: freeing needs that device current)
+        }
+    }
+    if (evict) cudaFree(evict);
+}
+// Smallest cached block of the current device with need <= bytes <= 2 * need, or null.
+void* cache_take(size_t need, size_t* got) {
+    int dev = 0;
+    if (need < kCacheMinBytes || cudaGetDevice(&dev) != cudaSuccess) return nullptr;
+    std::lock_guard<std::mutex> lock(cache_mutex());
+    std::vector<CachedBlock>& c = cache_blocks();
+    long best = -1;
+    for (size_t i = 0; i < c.size(); ++i)
+        if (c[i].device == dev && c[i].bytes >= need && c[i].bytes <= 2 * need && (best < 0 || c[i].bytes < c[(size_t)best].bytes)) best = (long)i;
+    if (best < 0) return nullptr;
+    void* p = c[(size_t)best].p; *got = c[(size_t)best].bytes;
+    c.erase(c.begin() + best);
+    return p;
+}
+
+// Grows a device buffer of the scene (the scene's device is current).
 template <class T>
 int ensure(T** p, size_t* cap, size_t need_elems) {
     if (*cap >= need_elems && *p) return RT_OK;
-    if (*p) cudaFree(*p);
+    if (*p) cache_put(*p, *cap * sizeof(T));
     *p = nullptr; *cap = 0;
+    size_t got = 0;
+    if (void* c = cache_take(need_elems * sizeof(T), &got)) { *p = (T*)c; *cap = got / sizeof(T); return RT_OK; }
     cudaError_t e = cudaMalloc((void**)p, need_elems * sizeof(T));
+    if (e != cudaSuccess) {                                  // out of memory: drop the cache and try once more
+        cudaGetLastError();
+        rt_release_device_cache();
+        e = cudaMalloc((void**)p, need_elems * sizeof(T));
+    }
     if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("cudaMalloc: ") + cudaGetErrorString(e));
     *cap = need_elems;
     return RT_OK;
@@ -506,7 +560,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     if (plan->variant != 1 && h.ray_depth > 255) return fail(RT_ERR_LIMIT, "ray_depth above 255 (the wavefront kernel packs the remaining depth in 8 bits; kernel_variant 10 has no limit)");
 
     if (h.ray_depth == 0) {                                    // rendering.rs:93-95: recursion_depth <= 0 is black, the scene is never looked at
-        a.chunk_size = s1 - s0; a.n_chunks = 1; a.n_pix_items = 0; a.total_items = 0;
+        a.n_chunks = 1; a.n_pix_items = 0; a.total_items = 0;
         const size_t n_pix0 = (size_t)h.width * (size_t)h.height;
         int rc0 = ensure(&s->layers, &s->layers_cap, n_pix0);
         if (rc0 != RT_OK) return rc0;
@@ -516,18 +570,23 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
         std::memset(ki, 0, sizeof(*ki));
         return RT_OK;
     }
-    plan->cfg = env_int("RT_WAVE_CFG", 2);
+    // resident-thread configuration (rt_kernels.cu RT_WAVE): 384 x 2 for scenes staged in shared memory; 352 x 2 for scenes read
+    // through L1 / L2 -- two warps fewer per SM bring the blocks under 97 KB of shared memory each, which lets the driver pick the
+    // 196 KB carve-out instead of 228 KB: 60 KB of L1 instead of 28 KB (measured: practice7_2 +4 %, practice7_3 +7 %)
+    const int cfg_env = env_int("RT_WAVE_CFG", -1);
+    const int cfg_smem = cfg_env >= 0 ? cfg_env : 2, cfg_gmem = cfg_env >= 0 ? cfg_env : 5;
     // sample chunks: enough (pixel, chunk) items to keep every resident path slot busy many times over
     int lanes = 0;
     if (plan->use_smem && placement == 0) {
         // automatic placement: staging the scene must not cost occupancy (a mid-size blob can push the block past half of the
         // SM's shared memory: one block per SM instead of two) -- fall back to the global-memory path in that case
         int with_smem = 0, without = 0;
-        cudaError_t es = rtd::render_resident_lanes(plan->variant, plan->cfg, true, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
+        cudaError_t es = rtd::render_resident_lanes(plan->variant, cfg_smem, true, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
         if (es != cudaSuccess) { cudaGetLastError(); with_smem = 0; }
-        CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, false, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &without));
-        if (with_smem < without) { plan->use_smem = false; a.blob = s->blob_dev; }
+        CUDA_TRY(rtd::render_resident_lanes(plan->variant, cfg_gmem, false, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &without));
+        if (with_smem < without * 9 / 10) { plan->use_smem = false; a.blob = s->blob_dev; }     // (352 x 2 keeps 8 % fewer lanes than 384 x 2: not a reason to leave shared memory)
     }
+    plan->cfg = plan->use_smem ? cfg_smem : cfg_gmem;
     CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
     const int n_samp = s1 - s0;
     // measured (B200): work items ~32x the resident path slots keep the end-of-frame tail short (512x512x1024 spp: +16 % over
@@ -539,8 +598,28 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     const size_t n_pix = (size_t)h.width * (size_t)h.height;
     const long long max_layers = std::max<long long>(1, (long long)((1ull << 30) / (n_pix * sizeof(float4))));
     if (want > max_layers) want = max_layers;
-    a.chunk_size = (int)((n_samp + want - 1) / want);
-    a.n_chunks = (n_samp + a.chunk_size - 1) / a.chunk_size;
+    // chunk schedule: `want` equal chunks, then a geometric tail (1/16, 1/32, 1/64, 1/64 of the samples) when the frame can afford the
+    // extra layers -- measured: one 128-sample item is 5.5 ms of a lane's time, which is what an 8-GPU frame (403 ms) used to lose
+    // at its end; with tail chunks of a few samples the last items take a fraction of a millisecond
+    int n_tail = 0, tail[4] = {0, 0, 0, 0};
+    if (env_int("RT_TAIL_CHUNKS", 1) && n_samp >= 64 && want + 4 <= std::min<long long>(max_layers, RT_MAX_CHUNKS)) {
+        tail[0] = n_samp / 16; tail[1] = n_samp / 32; tail[2] = n_samp / 64; tail[3] = n_samp / 64;
+        n_tail = 4;
+    }
+    if (want > RT_MAX_CHUNKS - n_tail) want = RT_MAX_CHUNKS - n_tail;
+    const int main_samples = n_samp - (tail[0] + tail[1] + tail[2] + tail[3]);
+    if (want > main_samples) want = std::max(1, main_samples);
+    std::vector<int32_t> cb(1, 0);
+    int pos = 0;
+    for (long long k = 0; k < want; ++k) {                     // near-equal split of the main part
+        pos = (int)((long long)main_samples * (k + 1) / want);
+        if (pos > cb.back()) cb.push_back(pos);
+    }
+    for (int k = 0; k < n_tail; ++k) if (tail[k] > 0) { pos += tail[k]; cb.push_back(pos); }
+    a.n_chunks = (int)cb.size() - 1;
+    if (!s->chunk_table) CUDA_TRY(cudaMalloc((void**)&s->chunk_table, (RT_MAX_CHUNKS + 1) * sizeof(int32_t)));
+    CUDA_TRY(cudaMemcpyAsync(s->chunk_table, cb.data(), cb.size() * sizeof(int32_t), cudaMemcpyHostToDevice, stream));   // pageable source: staged before the call returns
+    a.chunk_begin = s->chunk_table;
     const uint64_t total = (uint64_t)a.n_pix_items * (uint64_t)a.n_chunks;
     if (total >= 0xffffffffull) return fail(RT_ERR_LIMIT, "too many work items");
     a.total_items = (uint32_t)total;
@@ -561,6 +640,7 @@ int collect_stats(RtScene* s, const RenderPlan& plan, const rtd::KernelInfo& ki,
     st->kernel_launches = (uint64_t)launches;
     st->kernel = plan.variant; st->block_threads = ki.block; st->blocks_per_sm = ki.blocks_per_sm; st->grid_blocks = ki.grid;
     st->regs_per_thread = ki.regs; st->smem_bytes_per_block = ki.smem_bytes; st->scene_in_shared_memory = plan.use_smem ? 1 : 0;
+    st->n_chunks = plan.args.n_chunks;
     if (plan.stats) {
         unsigned long long v[rtd::RT_N_STATS];
         CUDA_TRY(cudaMemcpyAsync(v, s->stats_dev, sizeof(v), cudaMemcpyDeviceToHost, stream));
@@ -697,11 +777,27 @@ int rt_scene_create(const RtSceneDesc* d, int32_t device, RtScene** out) {
     return finish_create(s, out);
 }
 
+int rt_release_device_cache(void) {
+    std::vector<CachedBlock> all;
+    {
+        std::lock_guard<std::mutex> lock(cache_mutex());
+        all.swap(cache_blocks());
+    }
+    int prev = 0;
+    const bool have_prev = cudaGetDevice(&prev) == cudaSuccess;
+    for (const CachedBlock& b : all) { cudaSetDevice(b.device); cudaFree(b.p); }
+    if (have_prev) cudaSetDevice(prev);
+    return RT_OK;
+}
+
 void rt_scene_destroy(RtScene* s) {
     if (!s) return;
     if (s->stream || s->blob_dev) cudaSetDevice(s->device);
-    cudaFree(s->blob_dev); cudaFree(s->tri_d_dev); cudaFree(s->layers); cudaFree(s->accum); cudaFree(s->rgb_dev); cudaFree(s->lin_dev);
-    cudaFree(s->work_counter); cudaFree(s->stats_dev);
+    if (s->stream) cudaStreamSynchronize(s->stream);          // the frame buffers go back to the cache: nothing may still be writing them
+    cache_put(s->layers, s->layers_cap * sizeof(float4)); cache_put(s->accum, s->accum_cap * sizeof(float4));
+    cache_put(s->rgb_dev, s->rgb_cap); cache_put(s->lin_dev, s->lin_cap * sizeof(float));
+    cudaFree(s->blob_dev); cudaFree(s->tri_d_dev);
+    cudaFree(s->work_counter); cudaFree(s->stats_dev); cudaFree(s->chunk_table);
     for (int i = 0; i < 5; ++i) if (s->ev[i]) cudaEventDestroy(s->ev[i]);
     if (s->stream) cudaStreamDestroy(s->stream);
     delete s;
@@ -1040,6 +1136,7 @@ int render_multi_locked(RtScene* const* scenes, int32_t n, const RtRenderParams*
             for (int k = 0; k < 10; ++k) b[k] += a[k];                       // the ten uint64 counters
             total.kernel = one.kernel; total.block_threads = one.block_threads; total.blocks_per_sm = one.blocks_per_sm; total.grid_blocks = one.grid_blocks;
             total.regs_per_thread = one.regs_per_thread; total.smem_bytes_per_block = one.smem_bytes_per_block; total.scene_in_shared_memory = one.scene_in_shared_memory;
+            total.n_chunks = one.n_chunks;
         }
         total.kernel_launches += 2;                                           // resolve + (reduce or sum)
         float k = 0, t = 0;

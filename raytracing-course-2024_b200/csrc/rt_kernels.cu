@@ -196,8 +196,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS) render_kernel(const R
                     if (px < a.W && py < a.H && tile % a.shard_count == a.shard_index) {
                         have_item = true;
                         pix = (uint32_t)py * (uint32_t)a.W + (uint32_t)px;
-                        s_cur = a.s_begin + (int)chunk * a.chunk_size;
-                        s_stop = min(s_cur + a.chunk_size, a.s_end);
+                        s_cur = a.s_begin + __ldg(a.chunk_begin + chunk);
+                        s_stop = a.s_begin + __ldg(a.chunk_begin + chunk + 1);
                         acc = f3(0.f, 0.f, 0.f); acc_n = 0.f;
                     }
                 }
@@ -319,6 +319,8 @@ static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bo
         case 2: return RT_DISPATCH(launch_wave_t, , MODE, 384, 2);        \
         case 3: return RT_DISPATCH(launch_wave_t, , MODE, 256, 4);        \
         case 4: return RT_DISPATCH(launch_wave_t, , MODE, 512, 2);        \
+        case 5: return RT_DISPATCH(launch_wave_t, , MODE, 352, 2);        \
+        case 6: return RT_DISPATCH(launch_wave_t, , MODE, 320, 2);        \
         default: return RT_DISPATCH(launch_wave_t, , MODE, 256, 2);       \
     }
     if (a.L.general) {

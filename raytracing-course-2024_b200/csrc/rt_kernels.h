@@ -14,6 +14,7 @@ struct Camera {
     float two_over_w, two_over_h;  // 2/width, 2/height (rendering.rs:74-75 without a division per sample)
 };
 
+#define RT_MAX_CHUNKS 65536
 struct RenderArgs {
     const char* blob;            // device scene blob (global memory)
     SceneLayout L;
@@ -21,7 +22,11 @@ struct RenderArgs {
     float bg[3];
     int32_t W, H, ray_depth, max_attempts, n_comp;
     float inv_n_comp;            // 1 / n_comp (MixDistribution::pdf, distributions.rs:194-201)
-    int32_t s_begin, s_end, chunk_size, n_chunks;
+    int32_t s_begin, s_end, n_chunks;
+    // Sample chunks: chunk k renders samples [s_begin + chunk_begin[k], s_begin + chunk_begin[k+1]) of a pixel into layer k.  The first
+    // chunks are large and equal, the last ones shrink geometrically: work items are handed out in chunk order, so the items that are
+    // still running when the frame's work counter runs dry are short ones and the tail of the persistent kernel stays short.
+    const int32_t* chunk_begin;  // device array of n_chunks + 1 entries (read once per work item)
     uint32_t tiles_x, n_pix_items, total_items;
     uint32_t shard_index, shard_count;   // interleaved tile sharding: this launch owns tiles t with t % shard_count == shard_index (count >= 1)
     uint32_t stack_entries;

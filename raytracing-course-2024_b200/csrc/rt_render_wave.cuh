@@ -229,12 +229,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 if (state != ST_NONE && state != ST_NEED_ITEM) { xy = (uint32_t)pool.ldi(F_PIX, s); s_this = pool.ldi(F_S, s); }
                 if (ends) {
                     const int chunk = pool.ldi(F_CHUNK, s);
-                    const int s_stop = min(a.s_begin + (chunk + 1) * a.chunk_size, a.s_end);
+                    const int s_stop = a.s_begin + __ldg(a.chunk_begin + chunk + 1);
                     if (++s_this < s_stop) state = ST_GEN;
                     else {
                         const uint32_t pix = (xy >> 16) * (uint32_t)a.W + (xy & 0xffffu);
                         const float3 acc = pool.ld3(F_AX, s);
-                        const float n_done = (float)(s_stop - (a.s_begin + chunk * a.chunk_size));
+                        const float n_done = (float)(__ldg(a.chunk_begin + chunk + 1) - __ldg(a.chunk_begin + chunk));
                         a.layers[(size_t)chunk * n_pix + pix] = make_float4(acc.x, acc.y, acc.z, n_done);
                         state = ST_NEED_ITEM;
                     }
@@ -258,7 +258,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                             const uint32_t px = tx * 8u + (w & 7u), py = ty * 4u + (w >> 3);
                             if ((int)px < a.W && (int)py < a.H && tile % a.shard_count == a.shard_index) {
                                 xy = (py << 16) | px;
-                                s_this = a.s_begin + (int)chunk * a.chunk_size;
+                                s_this = a.s_begin + __ldg(a.chunk_begin + chunk);
                                 pool.sti(F_PIX, s, (int)xy);
                                 pool.sti(F_CHUNK, s, (int)chunk);
                                 pool.st3(F_AX, s, f3(0.f, 0.f, 0.f));

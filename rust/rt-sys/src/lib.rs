@@ -132,7 +132,7 @@ pub struct RtStats {
     pub regs_per_thread: i32,
     pub smem_bytes_per_block: i32,
     pub scene_in_shared_memory: i32,
-    pub reserved2: i32,
+    pub n_chunks: i32,
     pub render_ms: f64,
     pub reduce_ms: f64,
     pub resolve_ms: f64,
@@ -149,6 +149,7 @@ extern "C" {
     pub fn rt_scene_create(desc: *const RtSceneDesc, device: i32, out: *mut *mut RtScene) -> c_int;
     pub fn rt_scene_create2(desc: *const RtSceneDesc2, device: i32, out: *mut *mut RtScene) -> c_int;
     pub fn rt_scene_destroy(scene: *mut RtScene);
+    pub fn rt_release_device_cache() -> c_int;
     pub fn rt_scene_get_desc(scene: *const RtScene, out: *mut RtSceneDesc) -> c_int;
     pub fn rt_scene_get_desc2(scene: *const RtScene, out: *mut RtSceneDesc2) -> c_int;
     pub fn rt_scene_info(scene: *const RtScene, out: *mut RtSceneInfo) -> c_int;
