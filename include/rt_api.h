@@ -229,6 +229,13 @@ int rt_write_ppm(const char* path, int32_t width, int32_t height, const uint8_t*
 /* dump_rendered_to_png (src/main.rs:75-86): the same pixels as an 8-bit RGB PNG (self-contained writer, stored deflate). */
 int rt_write_png(const char* path, int32_t width, int32_t height, const uint8_t* rgb);
 
+/* ---- memory-safety instrument (compute-sanitizer is not available on every GPU pool) ---------------------------------- */
+/* In a library built with -DRT_DEBUG_BOUNDS (`make -C csrc debug` -> _build_dbg/librt_b200.so, same ABI) every shared-memory pool /
+ * queue / traversal-stack access, every scene-blob load, every primitive index and every framebuffer store of the kernels is
+ * range-checked and violations are counted per kind: counts[0..6] = pool slot, queue, stack, blob offset, primitive index, layer
+ * store, chunk index.  reset != 0 zeroes the counters.  A regular build returns RT_ERR_INVALID. */
+int rt_debug_bounds_violations(int32_t device, uint64_t* counts, int32_t reset);
+
 /* ---- roofline support ------------------------------------------------------------------------------------ */
 /* FFMA issue micro-benchmark on `device`: measured FP32 TFLOP/s (2 flop per FMA lane) and SM clock in MHz. */
 int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_mhz);

@@ -138,6 +138,14 @@ def _check(rc):
         raise RtError(rc, lib().rt_last_error().decode("utf-8", "replace"))
 
 
+def debug_bounds_violations(device=0, reset=False):
+    """Counters of the -DRT_DEBUG_BOUNDS build (RT_B200_LIB=.../_build_dbg/librt_b200.so); RtError in a regular build."""
+    out = (C.c_uint64 * 7)()
+    lib().rt_debug_bounds_violations.argtypes = [C.c_int32, C.POINTER(C.c_uint64), C.c_int32]
+    _check(lib().rt_debug_bounds_violations(device, out, 1 if reset else 0))
+    return dict(zip(("pool", "queue", "stack", "blob", "prim", "layer", "chunk"), [int(x) for x in out]))
+
+
 def release_device_cache():
     """Frees the frame buffers rt_scene_destroy parked for reuse (include/rt_api.h)."""
     _check(lib().rt_release_device_cache())

@@ -69,8 +69,10 @@ int main(int argc, char** argv) {
     const double secs = std::chrono::duration<double>(std::chrono::steady_clock::now() - start).count();
     std::printf("Rendering took %.6fs\n", secs);                                                   // main.rs:57-58
     const double msamples = (double)width * height * samples / secs / 1e6;
-    std::printf("{\"msamples_per_s\": %.3f, \"n_gpus\": %d, \"kernel_ms\": %.3f, \"total_ms\": %.3f, \"segments\": %llu}\n", msamples, n_gpus, stats.kernel_ms,
-                stats.total_ms, (unsigned long long)stats.segments);
+    std::printf("{\"msamples_per_s\": %.3f, \"n_gpus\": %d, \"kernel_ms\": %.3f, \"total_ms\": %.3f, \"render_ms\": %.3f, \"reduce_ms\": %.3f, \"resolve_ms\": %.3f", msamples,
+                n_gpus, stats.kernel_ms, stats.total_ms, stats.render_ms, stats.reduce_ms, stats.resolve_ms);
+    if (params.collect_stats) std::printf(", \"segments\": %llu", (unsigned long long)stats.segments);   // work counters exist only with RT_STATS=1
+    std::printf("}\n");
     std::printf("Dumping to %s\n", output_ppm);                                                    // main.rs:59
     if (rt_write_ppm(output_ppm, width, height, rendered.data(), (int)env_ll("RT_PPM_APPEND", 0)) != RT_OK) {
         std::fprintf(stderr, "error: %s\n", rt_last_error());

@@ -540,6 +540,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     if (p->tile_shard_count > 1 && (p->tile_shard_index < 0 || p->tile_shard_index >= p->tile_shard_count)) return fail(RT_ERR_INVALID, "tile_shard_index must be in [0, tile_shard_count)");
     a.node_min = std::min(32, std::max(1, env_int("RT_NODE_MIN", 10)));
     a.burst_exit = std::min(32, std::max(1, env_int("RT_BURST_EXIT", 20)));
+    a.debug_blob_limit = (uint32_t)std::max(0, env_int("RT_DEBUG_BLOB_LIMIT", 0));
     a.seed_lo = (uint32_t)(p->seed & 0xffffffffu); a.seed_hi = (uint32_t)(p->seed >> 32);
     plan->stats = p->collect_stats != 0;
     // kernel_variant = 10*kernel + scene placement: kernel 0 auto (= 3), 1 = v1 per-lane megakernel, 2 / 3 = v3 warp-local
@@ -997,6 +998,19 @@ int rt_multi_init(RtScene* const* scenes, int32_t n) {
     std::lock_guard<std::mutex> lock(multi_gpu_mutex());
     std::vector<int> devs;
     for (int g = 0; g < n; ++g) { if (!scenes[g] || !scenes[g]->blob_dev) return fail(RT_ERR_CUDA, "rt_multi_init: every scene must live on a CUDA device"); devs.push_back(scenes[g]->device); }
+    // frame buffers of the scenes' current frame size: the first frame must not pay ~1 GB of cudaMalloc per device inside the timing
+    // window of main.rs:54-58 (it did: the one-frame CLI ran 5 % behind the warmed-up bench loop on 8 GPUs)
+    for (int g = 0; g < n; ++g) {
+        RtScene* s = scenes[g];
+        if (s->host.width <= 0 || s->host.height <= 0) continue;
+        CUDA_TRY(cudaSetDevice(s->device));
+        const size_t n_pix = (size_t)s->host.width * (size_t)s->host.height;
+        const size_t layers = std::min<size_t>(8, std::max<size_t>(1, (size_t)((1ull << 30) / (n_pix * sizeof(float4)))));
+        int rc = ensure(&s->layers, &s->layers_cap, n_pix * layers);
+        if (rc == RT_OK) rc = ensure(&s->accum, &s->accum_cap, n_pix);
+        if (rc == RT_OK && g == 0) rc = ensure(&s->rgb_dev, &s->rgb_cap, n_pix * 3);
+        if (rc != RT_OK) return rc;
+    }
     if (n > 1 && ensure_comms(devs)) {                      // first collective = connection set-up: do it now, on a few floats
         NcclApi& nc = nccl_api();
         CommCache& cc = comm_cache();
@@ -1307,6 +1321,18 @@ int rt_write_png(const char* path, int32_t width, int32_t height, const uint8_t*
     const bool ok = std::fwrite(sig, 1, 8, f) == 8 && write_chunk(f, "IHDR", ihdr) && write_chunk(f, "IDAT", z) && write_chunk(f, "IEND", {});
     std::fclose(f);
     return ok ? RT_OK : fail(RT_ERR_IO, std::string("short write to ") + path);
+}
+
+int rt_debug_bounds_violations(int32_t device, uint64_t* counts, int32_t reset) {
+    if (!counts) return fail(RT_ERR_INVALID, "null argument");
+    CUDA_TRY(cudaSetDevice(device));
+    CUDA_TRY(cudaDeviceSynchronize());
+    unsigned long long v[rtd::RT_BOUNDS_KINDS];
+    const cudaError_t e = rtd::read_bounds_violations(v, reset);
+    if (e == cudaErrorNotSupported) { cudaGetLastError(); return fail(RT_ERR_INVALID, "not a -DRT_DEBUG_BOUNDS build (make -C csrc debug -> _build_dbg/librt_b200.so)"); }
+    if (e != cudaSuccess) return fail(RT_ERR_CUDA, std::string("rt_debug_bounds_violations: ") + cudaGetErrorString(e));
+    for (int k = 0; k < rtd::RT_BOUNDS_KINDS; ++k) counts[k] = v[k];
+    return RT_OK;
 }
 
 int rt_measure_fp32_peak(int32_t device, double* tflops, double* sm_mhz) {

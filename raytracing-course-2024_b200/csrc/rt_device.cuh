@@ -14,6 +14,20 @@ namespace rtd {
 #define RT_EPS_F 0.00001f /* geometry.rs:49 */
 #define RT_INF_F __int_as_float(0x7f800000)
 
+// ------------------------------------------------------------------------------------------------ debug bounds build
+// compute-sanitizer is closed on the B200 pool this repository is developed against, so memory safety gets its own instrument:
+// `make debug` compiles the same sources with -DRT_DEBUG_BOUNDS into _build_dbg/.  Every shared-memory pool / queue / stack access,
+// every scene-blob load, every primitive index and every layer store is then range-checked; a violation is COUNTED per kind (and the
+// access is still performed -- the point is to find it, on small cases, without killing the context) and read back through
+// rt_debug_bounds_violations().  tests/test_gpu_debug_bounds.py runs the parity workloads under this build and asserts all-zero.
+enum { RT_BOUNDS_POOL = 0, RT_BOUNDS_QUEUE, RT_BOUNDS_STACK, RT_BOUNDS_BLOB, RT_BOUNDS_PRIM, RT_BOUNDS_LAYER, RT_BOUNDS_CHUNK, RT_BOUNDS_KINDS };
+#ifdef RT_DEBUG_BOUNDS
+static __device__ unsigned long long g_bounds_violations[RT_BOUNDS_KINDS];
+#define RT_BOUNDS(cond, kind) do { if (!(cond)) atomicAdd(&rtd::g_bounds_violations[kind], 1ull); } while (0)
+#else
+#define RT_BOUNDS(cond, kind) ((void)0)
+#endif
+
 // ------------------------------------------------------------------------------------------------ float3 math
 RT_DEV float3 f3(float x, float y, float z) { return make_float3(x, y, z); }
 RT_DEV float3 f3(float4 v) { return make_float3(v.x, v.y, v.z); }
@@ -81,12 +95,17 @@ struct SceneLayout {
 
 struct SmemSpace {
     uint32_t base;  // shared-window address of the blob
+#ifdef RT_DEBUG_BOUNDS
+    uint32_t limit;  // blob bytes
+#endif
     RT_DEV float4 ld4(uint32_t off) const {
+        RT_BOUNDS((off & 15u) == 0u && off + 16u <= limit, RT_BOUNDS_BLOB);
         float4 v;
         asm("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(base + off));
         return v;
     }
     RT_DEV int2 ld2i(uint32_t off) const {
+        RT_BOUNDS((off & 7u) == 0u && off + 8u <= limit, RT_BOUNDS_BLOB);
         int2 v;
         asm("ld.shared.v2.s32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "r"(base + off));
         return v;
@@ -94,8 +113,17 @@ struct SmemSpace {
 };
 struct GmemSpace {
     const char* base;
-    RT_DEV float4 ld4(uint32_t off) const { return __ldg(reinterpret_cast<const float4*>(base + off)); }
-    RT_DEV int2 ld2i(uint32_t off) const { return __ldg(reinterpret_cast<const int2*>(base + off)); }
+#ifdef RT_DEBUG_BOUNDS
+    uint32_t limit;
+#endif
+    RT_DEV float4 ld4(uint32_t off) const {
+        RT_BOUNDS((off & 15u) == 0u && off + 16u <= limit, RT_BOUNDS_BLOB);
+        return __ldg(reinterpret_cast<const float4*>(base + off));
+    }
+    RT_DEV int2 ld2i(uint32_t off) const {
+        RT_BOUNDS((off & 7u) == 0u && off + 8u <= limit, RT_BOUNDS_BLOB);
+        return __ldg(reinterpret_cast<const int2*>(base + off));
+    }
 };
 
 // Per-thread traversal stack in shared memory, laid out [entry][thread]: bank = thread % 32 for every entry, so pushes
@@ -105,13 +133,23 @@ struct GmemSpace {
 struct SmemStack {
     uint32_t top;     // shared-window address of the next free entry of this thread
     uint32_t stride;  // bytes between entries = 4 * blockDim.x
-    RT_DEV void init(uint32_t thread_entry0, uint32_t stride_bytes) {
+#ifdef RT_DEBUG_BOUNDS
+    uint32_t lo, hi;  // addresses of this thread's entry 0 and of the entry past the last one
+#endif
+    RT_DEV void init(uint32_t thread_entry0, uint32_t stride_bytes, uint32_t entries = 0u) {
         stride = stride_bytes; top = thread_entry0 + stride_bytes;
+#ifdef RT_DEBUG_BOUNDS
+        lo = thread_entry0; hi = thread_entry0 + entries * stride_bytes;
+#else
+        (void)entries;
+#endif
         asm volatile("st.shared.s32 [%0], %1;" ::"r"(thread_entry0), "r"(RT_CUR_DONE));
     }
     RT_DEV void reset(uint32_t thread_entry0) { top = thread_entry0 + stride; }
-    RT_DEV void push(int v) { asm volatile("st.shared.s32 [%0], %1;" ::"r"(top), "r"(v)); top += stride; }
-    RT_DEV int pop() { int v; top -= stride; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(top)); return v; }
+    // `top` must stay in (lo, hi]: entry 0 (the sentinel) is never popped, the last entry may be pushed but not passed
+    RT_DEV void check() const { RT_BOUNDS(top > lo && top <= hi, RT_BOUNDS_STACK); }
+    RT_DEV void push(int v) { RT_BOUNDS(top < hi, RT_BOUNDS_STACK); asm volatile("st.shared.s32 [%0], %1;" ::"r"(top), "r"(v)); top += stride; }
+    RT_DEV int pop() { int v; top -= stride; RT_BOUNDS(top >= lo, RT_BOUNDS_STACK); asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(top)); return v; }
 };
 
 struct Counters { unsigned long long node_tests, tri_tests, light_tri_tests; };
@@ -204,6 +242,9 @@ RT_DEV void pair_step(const Space& sp, uint32_t nodes, const RaySetup& r, float 
         "}"
         : "+r"(cur), "+r"(st.top)
         : "f"(t0), "f"(t1), "f"(e0), "f"(e1), "r"(ch.x), "r"(ch.y), "r"(st.stride), "f"(ORDERED ? t0 : t1));
+#ifdef RT_DEBUG_BOUNDS
+    RT_BOUNDS(st.top >= st.lo && st.top <= st.hi, RT_BOUNDS_STACK);      // (== lo: the sentinel was popped, the walk is over)
+#endif
 }
 
 // Two-sided ray/triangle test with inclusive edges: u >= 0, v >= 0, u + v <= 1, t > 0 (geometry.rs:109-113).  The

@@ -149,9 +149,12 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS) render_kernel(const R
         for (uint32_t i = threadIdx.x; i < a.L.total_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
         __syncthreads();
     }
-    const Space sp = SpaceMaker<Space>::make(a.blob, smem_base + stack_bytes);
+    Space sp = SpaceMaker<Space>::make(a.blob, smem_base + stack_bytes);
+#ifdef RT_DEBUG_BOUNDS
+    sp.limit = a.debug_blob_limit ? a.debug_blob_limit : a.L.total_bytes;
+#endif
     const SceneLayout& L = a.L;
-    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u);
+    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u, a.stack_entries);
     const unsigned lane = threadIdx.x & 31u;
     const uint2 key = make_uint2(a.seed_lo, a.seed_hi);
     const float3 bg = f3(a.bg[0], a.bg[1], a.bg[2]);
@@ -173,6 +176,8 @@ __global__ void __launch_bounds__(RT_BLOCK, RT_MIN_BLOCKS) render_kernel(const R
 
     for (;;) {
         if (!alive && have_item && s_cur >= s_stop) {           // item done: one store per (pixel, chunk)
+            RT_BOUNDS(chunk < (uint32_t)a.n_chunks, RT_BOUNDS_CHUNK);
+            RT_BOUNDS((size_t)pix < n_pix, RT_BOUNDS_LAYER);
             a.layers[(size_t)chunk * n_pix + pix] = make_float4(acc.x, acc.y, acc.z, acc_n);
             have_item = false;
         }
@@ -434,8 +439,11 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const char* blob, const
                                                          double* __restrict__ hits) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u);
+    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u, stack_entries);
     GmemSpace sp; sp.base = blob;
+#ifdef RT_DEBUG_BOUNDS
+    sp.limit = L.total_bytes;
+#endif
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
     double od[3] = {rays[6 * i], rays[6 * i + 1], rays[6 * i + 2]}, dd[3] = {rays[6 * i + 3], rays[6 * i + 4], rays[6 * i + 5]};
@@ -529,8 +537,11 @@ __global__ void __launch_bounds__(128) eval_kernel(const char* blob, const Scene
                                                    const float* __restrict__ in, long long n, float* __restrict__ out) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     const uint32_t smem_base = (uint32_t)__cvta_generic_to_shared(smem_raw);
-    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u);
+    SmemStack st; st.init(smem_base + threadIdx.x * 4u, blockDim.x * 4u, stack_entries);
     GmemSpace sp; sp.base = blob;
+#ifdef RT_DEBUG_BOUNDS
+    sp.limit = L.total_bytes;
+#endif
     Counters cnt; cnt.node_tests = 0; cnt.tri_tests = 0; cnt.light_tri_tests = 0;
     const long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x;
     if (i >= n) return;
@@ -598,6 +609,23 @@ cudaError_t launch_eval(const char* blob, const SceneLayout& L, uint32_t stack_e
     if (e != cudaSuccess) return e;
     eval_kernel<<<(int)((n + block - 1) / block), block, smem, stream>>>(blob, L, stack_entries, fn, eval_in_width(fn), eval_out_width(fn), in, n, out);
     return cudaGetLastError();
+}
+
+// ------------------------------------------------------------------------------------------------ debug bounds counters
+// out: RT_BOUNDS_KINDS counters of this translation unit's kernels (all the kernels that touch scene data live here).  Returns
+// cudaErrorNotSupported in a regular build.  reset != 0 zeroes them afterwards.
+cudaError_t read_bounds_violations(unsigned long long* out, int reset) {
+#ifdef RT_DEBUG_BOUNDS
+    cudaError_t e = cudaMemcpyFromSymbol(out, g_bounds_violations, sizeof(unsigned long long) * RT_BOUNDS_KINDS);
+    if (e == cudaSuccess && reset) {
+        unsigned long long zero[RT_BOUNDS_KINDS] = {0};
+        e = cudaMemcpyToSymbol(g_bounds_violations, zero, sizeof(zero));
+    }
+    return e;
+#else
+    (void)out; (void)reset;
+    return cudaErrorNotSupported;
+#endif
 }
 
 // ------------------------------------------------------------------------------------------------ FP32 issue micro-benchmark

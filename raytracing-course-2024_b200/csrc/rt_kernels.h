@@ -32,6 +32,7 @@ struct RenderArgs {
     uint32_t stack_entries;
     int32_t node_min;            // v3 phased bursts: box-pair steps run while at least this many lanes want one
     int32_t burst_exit;          // v3: a trace burst ends when this many lanes of the warp have finished their ray (1..32)
+    uint32_t debug_blob_limit;   // RT_DEBUG_BOUNDS builds: blob bytes the loads are checked against (0 = L.total_bytes; RT_DEBUG_BLOB_LIMIT lowers it to prove the instrument fires)
     uint32_t seed_lo, seed_hi;
     float4* layers;              // n_chunks x W*H  (rgb sums, sample count)
     unsigned int* work_counter;  // zeroed before launch
@@ -60,6 +61,7 @@ cudaError_t launch_primary_rays(const Camera& cam, int W, int H, const int32_t* 
 cudaError_t launch_eval(const char* blob, const SceneLayout& L, uint32_t stack_entries, int fn, const float* in, long long n, float* out, cudaStream_t stream);
 cudaError_t launch_ffma(int blocks, int threads, int iters, float* sink, cudaStream_t stream);
 
+cudaError_t read_bounds_violations(unsigned long long* out, int reset);   // RT_DEBUG_BOUNDS builds only (rt_device.cuh)
 int eval_in_width(int fn);
 int eval_out_width(int fn);
 

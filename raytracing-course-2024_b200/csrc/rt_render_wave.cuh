@@ -41,7 +41,10 @@ enum { ST_NEED_ITEM = 0, ST_ENDED = 1, ST_GEN = 2, ST_TRACE = 3, ST_RETRY = 4, S
 
 struct Pool {
     uint32_t base;
-    RT_DEV uint32_t at(int f, int s) const { return base + (uint32_t)(f * RT_POOL_SLOTS + s) * 4u; }
+    RT_DEV uint32_t at(int f, int s) const {
+        RT_BOUNDS(f >= 0 && f < NF && s >= 0 && s < RT_POOL_SLOTS, RT_BOUNDS_POOL);
+        return base + (uint32_t)(f * RT_POOL_SLOTS + s) * 4u;
+    }
     RT_DEV float ldf(int f, int s) const { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(at(f, s))); return v; }
     RT_DEV int ldi(int f, int s) const { int v; asm volatile("ld.shared.s32 %0, [%1];" : "=r"(v) : "r"(at(f, s))); return v; }
     RT_DEV void stf(int f, int s, float v) const { asm volatile("st.shared.f32 [%0], %1;" ::"r"(at(f, s)), "f"(v)); }
@@ -49,7 +52,10 @@ struct Pool {
     RT_DEV float3 ld3(int f, int s) const { return f3(ldf(f, s), ldf(f + 1, s), ldf(f + 2, s)); }
     RT_DEV void st3(int f, int s, float3 v) const { stf(f, s, v.x); stf(f + 1, s, v.y); stf(f + 2, s, v.z); }
     // queues: q = 0 (TQ) or 1 (SQ), pos in [0, RT_POOL_SLOTS)
-    RT_DEV uint32_t qat(int q, int pos) const { return base + RT_POOL_SLOTS * NF * 4u + (uint32_t)(q * RT_POOL_SLOTS + pos); }
+    RT_DEV uint32_t qat(int q, int pos) const {
+        RT_BOUNDS((q == 0 || q == 1) && pos >= 0 && pos < RT_POOL_SLOTS, RT_BOUNDS_QUEUE);
+        return base + RT_POOL_SLOTS * NF * 4u + (uint32_t)(q * RT_POOL_SLOTS + pos);
+    }
     RT_DEV int qld(int q, int pos) const { int v; asm volatile("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(qat(q, pos))); return v; }
     RT_DEV void qst(int q, int pos, int v) const { asm volatile("st.shared.u8 [%0], %1;" ::"r"(qat(q, pos)), "r"(v)); }
 };
@@ -73,9 +79,12 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
         for (uint32_t i = threadIdx.x; i < a.L.total_bytes / 16u; i += blockDim.x) dst[i] = __ldg(src + i);
         __syncthreads();
     }
-    const Space sp = SpaceMaker<Space>::make(a.blob, smem_base + stack_bytes);
+    Space sp = SpaceMaker<Space>::make(a.blob, smem_base + stack_bytes);
+#ifdef RT_DEBUG_BOUNDS
+    sp.limit = a.debug_blob_limit ? a.debug_blob_limit : a.L.total_bytes;
+#endif
     const SceneLayout& L = a.L;
-    SmemStack st; st.init(smem_base + threadIdx.x * 4u, BLOCK * 4u);
+    SmemStack st; st.init(smem_base + threadIdx.x * 4u, BLOCK * 4u, a.stack_entries);
     const uint32_t stack0 = smem_base + threadIdx.x * 4u;
     const unsigned lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     const unsigned lt_mask = (1u << lane) - 1u;
@@ -212,6 +221,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                         if (bg_nonzero) pool.st3(F_AX, s, pool.ld3(F_AX, s) + T * bg);
                         ends = true;
                     } else {
+                        RT_BOUNDS(tri < L.n_tris + L.n_planes || (L.n_tris == 0 && tri == 0), RT_BOUNDS_PRIM);
                         n0 = sp.ld4(L.sh_n0 + (uint32_t)tri * 16u);
                         mat_id = __float_as_int(n0.w);
                         if (attempt == 0) {
@@ -235,6 +245,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                         const uint32_t pix = (xy >> 16) * (uint32_t)a.W + (xy & 0xffffu);
                         const float3 acc = pool.ld3(F_AX, s);
                         const float n_done = (float)(__ldg(a.chunk_begin + chunk + 1) - __ldg(a.chunk_begin + chunk));
+                        RT_BOUNDS(chunk >= 0 && chunk < a.n_chunks, RT_BOUNDS_CHUNK);
+                        RT_BOUNDS((size_t)pix < n_pix, RT_BOUNDS_LAYER);
                         a.layers[(size_t)chunk * n_pix + pix] = make_float4(acc.x, acc.y, acc.z, n_done);
                         state = ST_NEED_ITEM;
                     }

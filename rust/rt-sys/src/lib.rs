@@ -170,6 +170,7 @@ extern "C" {
 
     pub fn rt_write_ppm(path: *const c_char, width: i32, height: i32, rgb: *const u8, append: i32) -> c_int;
     pub fn rt_write_png(path: *const c_char, width: i32, height: i32, rgb: *const u8) -> c_int;
+    pub fn rt_debug_bounds_violations(device: i32, counts: *mut u64, reset: i32) -> c_int;
     pub fn rt_measure_fp32_peak(device: i32, tflops: *mut f64, sm_mhz: *mut f64) -> c_int;
 }
 
