@@ -96,11 +96,12 @@ enum { SHAPE_TRIANGLE = 0, SHAPE_BOX = 1, SHAPE_ELLIPSOID = 2, SHAPE_PLANE = 3 }
 enum { MAT_PBR = 0, MAT_DIELECTRIC = 1 };
 struct Quat { Fp i, j, k, w; };
 struct Primitive {
-    int kind;
     V3 a, b, c, a_norm, b_norm, c_norm;   // Shape3D::Triangle
+    int kind; bool identity;              // identity: rotation == 1 and position == 0 -> the Object3D transforms are exact no-ops
+    int mat_kind, orig_id;
+    Material material; V3 emission; Aabb aabb;
     V3 s;                                 // Shape3D::Box { s } | ellipsoid radii | plane normal
-    V3 position; Quat rotation; bool identity;   // Object3D (identity: rotation == 1 and position == 0 -> the transforms are exact no-ops)
-    Aabb aabb; Material material; Fp ior; int mat_kind; V3 emission; int orig_id;
+    V3 position; Quat rotation; Fp ior;   // Object3D position / rotation, Primitive.ior
 };
 
 struct Counters {
@@ -110,8 +111,8 @@ struct Counters {
 
 // ------------------------------------------------------------------------------------------------ geometry
 // [REF] geometry.rs:93-138  intersect_with_triangle: solve [b-a, c-a, -d] (u,v,t)^T = o - a with Matrix3::try_inverse.
-static bool intersect_with_triangle(const Ray& ray, Fp upper_bound, const Primitive& p, Intersection* out,
-                                    Fp* uo = nullptr, Fp* vo = nullptr) {
+static inline __attribute__((always_inline)) bool intersect_with_triangle(const Ray& ray, Fp upper_bound, const Primitive& p, Intersection* out,
+                                                                          Fp* uo = nullptr, Fp* vo = nullptr) {
     V3 c0 = p.b - p.a, c1 = p.c - p.a, c2 = -ray.direction;
     Fp m11 = c0.x, m21 = c0.y, m31 = c0.z;
     Fp m12 = c1.x, m22 = c1.y, m32 = c1.z;
@@ -397,8 +398,8 @@ static int validate_bvh(const BvhTree& t) {
     return bad;
 }
 
-// bvh.rs:168-172: all hits of one primitive (ArrayVec<_, 2>), the object-space ray and the primitive.  hit == hits[0].
-struct BvhIntersection { Intersection hit; Intersection hits[2]; int n_hits; Ray rotated_ray; const Primitive* primitive; Fp u, v; };
+// bvh.rs:168-172: all hits of one primitive (ArrayVec<_, 2>; hits[0] is the one that competes), the primitive, the object-space ray.
+struct BvhIntersection { Intersection hits[2]; int n_hits; const Primitive* primitive; Fp u, v; Ray rotated_ray; };
 
 // bvh.rs:249-297 nearest: unordered DFS (left, then right), prune iff best < t_box_first && entering, leaf
 // prims tested with upper = +inf; a primitive competes with its FIRST hit only (points.0[0], bvh.rs:269) under strict `<`.
@@ -410,12 +411,20 @@ static void nearest_impl(const Ray& ray, const BvhTree& t, size_t idx, BvhInters
     if (*shortest < tb && outer) return;
     if (node.left_child_index == NO_CHILD) {
         for (size_t i = node.content_start; i < node.content_start + node.content_length; ++i) {
-            Intersection h[2]; Fp u = 1.0 / 3.0, v = 1.0 / 3.0; Ray rr;
+            const Primitive& prim = t.primitives[i];
             ++c->tri_tests;
-            int n = intersect_ray_with_object3d_all_points(ray, t.primitives[i], h, &rr, FP_INF, &u, &v);
+            if (prim.kind == SHAPE_TRIANGLE && prim.identity) {          // what every glTF primitive is: the transforms are exact no-ops (same arithmetic as below)
+                Intersection h; Fp u, v;
+                if (intersect_with_triangle(ray, FP_INF, prim, &h, &u, &v) && h.offset < *shortest) {
+                    *shortest = h.offset; res->hits[0] = h; res->n_hits = 1; res->primitive = &prim; res->u = u; res->v = v; *found = true;
+                }
+                continue;
+            }
+            Intersection h[2]; Fp u = 1.0 / 3.0, v = 1.0 / 3.0; Ray rr;
+            int n = intersect_ray_with_object3d_all_points(ray, prim, h, &rr, FP_INF, &u, &v);
             if (n > 0 && h[0].offset < *shortest) {
-                *shortest = h[0].offset; res->hit = h[0]; res->hits[0] = h[0]; res->hits[1] = h[1]; res->n_hits = n; res->rotated_ray = rr;
-                res->primitive = &t.primitives[i]; res->u = u; res->v = v; *found = true;
+                *shortest = h[0].offset; res->hits[0] = h[0]; res->hits[1] = h[1]; res->n_hits = n; res->rotated_ray = rr;
+                res->primitive = &prim; res->u = u; res->v = v; *found = true;
             }
         }
     } else {
@@ -439,10 +448,20 @@ static void all_points_impl(const Ray& ray, const BvhTree& t, size_t idx, std::v
     if (!get_aabb_intersection(ray, node.aabb, &tb, &outer)) return;       // intersects() :146-155
     if (node.left_child_index == NO_CHILD) {
         for (size_t i = node.content_start; i < node.content_start + node.content_length; ++i) {
-            BvhIntersection bi; bi.u = bi.v = 1.0 / 3.0;
+            const Primitive& prim = t.primitives[i];
             ++c->light_tri_tests;
-            bi.n_hits = intersect_ray_with_object3d_all_points(ray, t.primitives[i], bi.hits, &bi.rotated_ray, FP_INF, &bi.u, &bi.v);
-            if (bi.n_hits > 0) { bi.hit = bi.hits[0]; bi.primitive = &t.primitives[i]; out->push_back(bi); }
+            if (prim.kind == SHAPE_TRIANGLE && prim.identity) {          // identity triangle: no transform, one hit, the local point is never read
+                Intersection h; Fp u, v;
+                if (intersect_with_triangle(ray, FP_INF, prim, &h, &u, &v)) {
+                    out->emplace_back();
+                    BvhIntersection& bi = out->back();
+                    bi.hits[0] = h; bi.n_hits = 1; bi.primitive = &prim; bi.u = u; bi.v = v;
+                }
+                continue;
+            }
+            BvhIntersection bi; bi.u = bi.v = 1.0 / 3.0;
+            bi.n_hits = intersect_ray_with_object3d_all_points(ray, prim, bi.hits, &bi.rotated_ray, FP_INF, &bi.u, &bi.v);
+            if (bi.n_hits > 0) { bi.primitive = &prim; out->push_back(bi); }
         }
     } else {
         all_points_impl(ray, t, node.left_child_index, out, c);
@@ -579,7 +598,8 @@ static Fp multiple_light_pdf(const Scene& sc, V3 point, V3 l, Counters* c) {
         for (int k = 0; k < bi.n_hits; ++k) {
             const Intersection& x = bi.hits[k];
             V3 global = ray.origin + x.offset * ray.direction;
-            Fp local_pdf = get_local_pdf(*bi.primitive, bi.rotated_ray.origin + bi.rotated_ray.direction * x.offset);
+            const bool flat = bi.primitive->kind == SHAPE_TRIANGLE;            // the local point matters for ellipsoids only
+            Fp local_pdf = get_local_pdf(*bi.primitive, flat ? v3(0, 0, 0) : bi.rotated_ray.origin + bi.rotated_ray.direction * x.offset);
             V3 vec = global - point;
             V3 omega = normalize(vec);
             sum += local_pdf * (norm_squared(vec) / std::fabs(dot(x.normal_geometry, omega)));
@@ -711,12 +731,12 @@ static Ray primary_ray(const Scene& sc, int x, int y, Fp xi1, Fp xi2) {       //
 static bool intersect_ray_with_scene(const Ray& ray, const Scene& sc, BvhIntersection* bi, Counters* c) {
     Fp latest = FP_INF;
     bool found = intersect_with_bvh_nearest_point(ray, sc.bvh_finite_primitives, bi, c);
-    if (found) latest = bi->hit.offset;
+    if (found) latest = bi->hits[0].offset;
     for (const Primitive& plane : sc.infinite_primitives) {
         Intersection x;
         ++c->tri_tests;
         if (intersect_ray_with_object3d(ray, plane, latest, &x) && x.offset < latest) {
-            latest = x.offset; bi->hit = x; bi->hits[0] = x; bi->n_hits = 1; bi->primitive = &plane; bi->u = bi->v = 1.0 / 3.0; found = true;
+            latest = x.offset; bi->hits[0] = x; bi->n_hits = 1; bi->primitive = &plane; bi->u = bi->v = 1.0 / 3.0; found = true;
         }
     }
     return found;
@@ -746,9 +766,9 @@ static V3 get_ray_color(const Ray& ray, const Scene& sc, int depth, Rng* rng, Co
     if (!intersect_ray_with_scene(ray, sc, &bi, c)) return sc.bg_color;       // :96, :125
     ++c->vertices;
     const Primitive& prim = *bi.primitive;
-    V3 corrected_point = ray.origin + ray.direction * (bi.hit.offset - EPS);
+    V3 corrected_point = ray.origin + ray.direction * (bi.hits[0].offset - EPS);
     V3 total = prim.emission;
-    V3 n = bi.hit.normal_geometry;
+    V3 n = bi.hits[0].normal_geometry;
     V3 v = -normalize(ray.direction);
     if (prim.mat_kind == MAT_DIELECTRIC) {
         // [OWN SPEC] (reference HEAD has no transmissive material, only the dead fields `ior` scene.rs:18
@@ -757,13 +777,13 @@ static V3 get_ray_color(const Ray& ray, const Scene& sc, int depth, Rng* rng, Co
         // refraction; the refracted ray starts EPS BEHIND the surface and is tinted by the base colour when it ENTERS.
         ++c->attempts;
         V3 dir;
-        bool reflect = !dielectric_sample(n, v, prim.ior, bi.hit.is_outer_to_inner, rng->gen_f64(), &dir);
+        bool reflect = !dielectric_sample(n, v, prim.ior, bi.hits[0].is_outer_to_inner, rng->gen_f64(), &dir);
         Ray next; V3 weight = v3(1, 1, 1);
         next.direction = dir;
         if (reflect) next.origin = corrected_point;
         else {
-            next.origin = ray.origin + ray.direction * (bi.hit.offset + EPS);
-            if (bi.hit.is_outer_to_inner) weight = prim.material.base_color_factor;
+            next.origin = ray.origin + ray.direction * (bi.hits[0].offset + EPS);
+            if (bi.hits[0].is_outer_to_inner) weight = prim.material.base_color_factor;
         }
         return total + cmul(get_ray_color(next, sc, depth - 1, rng, c), weight);
     }
@@ -772,7 +792,7 @@ static V3 get_ray_color(const Ray& ray, const Scene& sc, int depth, Rng* rng, Co
         ++c->attempts;
         l = mix_sample(sc, corrected_point, n, v, prim.material, rng, c);
         pdf = mix_pdf(sc, corrected_point, n, l, v, prim.material, c);
-        if (pdf > 0.0 && dot(l, bi.hit.normal_shading) > 0.0) break;
+        if (pdf > 0.0 && dot(l, bi.hits[0].normal_shading) > 0.0) break;
         // the reference spins for ever when no direction can pass (e.g. an object rotated by ~180 degrees: normal_shading is
         // not rotated back); sc.max_attempts > 0 ends the path like the device's attempt cap does (0 = unbounded, the reference)
         if (sc.max_attempts > 0 && attempt >= sc.max_attempts) { ++c->attempt_cap_hits; return total; }
@@ -980,7 +1000,7 @@ void or_trace_primary(void* h, const double* rays, int64_t n, int32_t* tri_id, d
         BvhIntersection bi; ++c.segments;
         bool hit = intersect_ray_with_scene(r, *sc, &bi, &c);
         tri_id[i] = hit ? bi.primitive->orig_id : -1;
-        t[i] = hit ? bi.hit.offset : FP_INF;
+        t[i] = hit ? bi.hits[0].offset : FP_INF;
         if (u) u[i] = hit ? bi.u : 0.0;
         if (v) v[i] = hit ? bi.v : 0.0;
         if (second_t) {
@@ -1005,8 +1025,8 @@ void or_trace_hits(void* h, const double* rays, int64_t n, double* out) {
         Ray r; r.origin = rd3(rays + 6 * i); r.direction = rd3(rays + 6 * i + 3);
         BvhIntersection bi; double* o = out + 9 * i;
         if (intersect_ray_with_scene(r, *sc, &bi, &c)) {
-            o[0] = bi.hit.offset; wr3(o + 1, bi.hit.normal_geometry); wr3(o + 4, bi.hit.normal_shading); o[7] = (double)bi.primitive->orig_id;
-            o[8] = bi.hit.is_outer_to_inner ? 1.0 : 0.0;
+            o[0] = bi.hits[0].offset; wr3(o + 1, bi.hits[0].normal_geometry); wr3(o + 4, bi.hits[0].normal_shading); o[7] = (double)bi.primitive->orig_id;
+            o[8] = bi.hits[0].is_outer_to_inner ? 1.0 : 0.0;
         } else { o[0] = FP_INF; for (int k = 1; k < 7; ++k) o[k] = 0.0; o[7] = -1.0; o[8] = 0.0; }
     }
 }

@@ -134,3 +134,21 @@ def test_render_is_deterministic_and_seedable(oracle):
     # row subset renders only those rows
     d = sc.render(seed=0, n_threads=2, rows=(4, 12, 4))
     assert np.array_equal(d["mean"][4], a["mean"][4]) and np.array_equal(d["mean"][8], a["mean"][8]) and not d["mean"][5].any()
+
+
+def test_oracle_renders_are_bit_stable(oracle):
+    """The oracle is the checker: its arithmetic must not drift when it is refactored (round 2 generalised it from triangles to
+    Object3D primitives).  48x32x32-spp renders (seed 0 = the reference's per-row xoshiro seeding) are pinned by a hash of the
+    f64 image and by two work counters; the practice7_* entries are the values the ROUND-1 oracle produced (checked against the
+    round-1 sources when the generalisation landed), the text-scene entries pin the own-spec paths from round 2 on."""
+    import hashlib
+    import json
+    import os
+    from conftest import GOLDEN, SCENES
+    want = json.load(open(os.path.join(GOLDEN, "oracle_checksums.json")))
+    for name, w in want.items():
+        g = os.path.join(SCENES, name + ".gltf")
+        fl = oracle.convert_gltf_to_scene(g, 48, 32, 32) if os.path.exists(g) else oracle.parse_text_scene(os.path.join(SCENES, name + ".txt"), 48, 32, 32)
+        r = oracle.OracleScene(fl).render(seed=0, n_threads=3)
+        got = {"sha16": hashlib.sha256(r["mean"].tobytes()).hexdigest()[:16], "attempts": r["stats"]["attempts"], "node_tests": r["stats"]["node_tests"]}
+        assert got == w, (name, got, w)
