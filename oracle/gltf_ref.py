@@ -123,25 +123,38 @@ def _node_transform(node):
     """(matrix f64 4x4 row-major, rotation (x,y,z,w) as f32 values) of a node, like node.transform()."""
     if "matrix" in node:
         m = np.array(node["matrix"], dtype=F32).reshape(4, 4).T.astype(np.float64)
-        # Transform::Matrix.decomposed(): rotation extracted from the normalised upper 3x3 (gltf crate).
-        a = np.array(node["matrix"], dtype=F32).reshape(4, 4).T[:3, :3].astype(np.float64)
-        sc = np.linalg.norm(a, axis=0)
-        if np.linalg.det(a) < 0:
-            sc = -sc
-        rot = a / sc
-        tr = np.trace(rot)
-        if tr > 0:
-            s_ = 0.5 / np.sqrt(tr + 1.0)
-            q = [(rot[2, 1] - rot[1, 2]) * s_, (rot[0, 2] - rot[2, 0]) * s_, (rot[1, 0] - rot[0, 1]) * s_, 0.25 / s_]
+        # gltf crate 1.x `Transform::Matrix { matrix }.decomposed()` (scene/mod.rs; restated from its published source -- the crate is
+        # not vendored and there is no Cargo.lock): ALL in f32.  i = upper 3x3 by columns; sx = |i.x|, sy = |i.y|,
+        # sz = signum(det i) * |i.z| (a mirror goes to the z scale only); columns divided by their scale (multiply by 1/s);
+        # rotation = Quaternion::from_matrix(i) (the cgmath branch order: trace >= 0, then the largest diagonal element).
+        c = np.array(node["matrix"], dtype=F32).reshape(4, 4)[:3, :3].copy()          # c[k] = column k (x, y, z components)
+        mag = lambda v: F32(np.sqrt(F32(F32(F32(v[0] * v[0]) + F32(v[1] * v[1])) + F32(v[2] * v[2]))))   # noqa: E731
+        x, y, z = c[0], c[1], c[2]
+        det = F32(F32(F32(x[0] * F32(F32(y[1] * z[2]) - F32(z[1] * y[2]))) - F32(y[0] * F32(F32(x[1] * z[2]) - F32(z[1] * x[2])))) + F32(z[0] * F32(F32(x[1] * y[2]) - F32(y[1] * x[2]))))
+        sx, sy = mag(x), mag(y)
+        sz = F32(F32(np.copysign(F32(1.0), det)) * mag(z))                               # f32::signum: +-1 (also for +-0)
+        x = np.array([F32(v * F32(F32(1.0) / sx)) for v in x], dtype=F32)
+        y = np.array([F32(v * F32(F32(1.0) / sy)) for v in y], dtype=F32)
+        z = np.array([F32(v * F32(F32(1.0) / sz)) for v in z], dtype=F32)
+        trace = F32(F32(x[0] + y[1]) + z[2])
+        h = F32(0.5)
+        if trace >= 0:
+            s_ = F32(np.sqrt(F32(F32(1.0) + trace)))
+            w = F32(h * s_); s_ = F32(h / s_)
+            q = [F32(F32(y[2] - z[1]) * s_), F32(F32(z[0] - x[2]) * s_), F32(F32(x[1] - y[0]) * s_), w]
+        elif x[0] > y[1] and x[0] > z[2]:
+            s_ = F32(np.sqrt(F32(F32(F32(x[0] - y[1]) - z[2]) + F32(1.0))))
+            qx = F32(h * s_); s_ = F32(h / s_)
+            q = [qx, F32(F32(y[0] + x[1]) * s_), F32(F32(x[2] + z[0]) * s_), F32(F32(y[2] - z[1]) * s_)]
+        elif y[1] > z[2]:
+            s_ = F32(np.sqrt(F32(F32(F32(y[1] - x[0]) - z[2]) + F32(1.0))))
+            qy = F32(h * s_); s_ = F32(h / s_)
+            q = [F32(F32(y[0] + x[1]) * s_), qy, F32(F32(z[1] + y[2]) * s_), F32(F32(z[0] - x[2]) * s_)]
         else:
-            i = int(np.argmax(np.diag(rot)))
-            j, k = (i + 1) % 3, (i + 2) % 3
-            s_ = 2.0 * np.sqrt(1.0 + rot[i, i] - rot[j, j] - rot[k, k])
-            q = [0.0, 0.0, 0.0, (rot[k, j] - rot[j, k]) / s_]
-            q[i] = 0.25 * s_
-            q[j] = (rot[j, i] + rot[i, j]) / s_
-            q[k] = (rot[k, i] + rot[i, k]) / s_
-        return m, [float(F32(c)) for c in q]
+            s_ = F32(np.sqrt(F32(F32(F32(z[2] - x[0]) - y[1]) + F32(1.0))))
+            qz = F32(h * s_); s_ = F32(h / s_)
+            q = [F32(F32(x[2] + z[0]) * s_), F32(F32(z[1] + y[2]) * s_), qz, F32(F32(x[1] - y[0]) * s_)]
+        return m, [float(c_) for c_ in q]
     t = node.get("translation", [0.0, 0.0, 0.0])
     r = node.get("rotation", [0.0, 0.0, 0.0, 1.0])
     s = node.get("scale", [1.0, 1.0, 1.0])

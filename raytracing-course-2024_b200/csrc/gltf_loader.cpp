@@ -218,27 +218,35 @@ struct Builder {
             float cm[16];
             for (int a = 0; a < 16; ++a) cm[a] = f32_of(mv->at((size_t)a));
             for (int r = 0; r < 4; ++r) for (int c = 0; c < 4; ++c) local->m[r][c] = (double)cm[c * 4 + r];
-            // Transform::Matrix.decomposed(): rotation of the scale-normalised upper 3x3
-            double a[3][3], sc3[3];
-            for (int c = 0; c < 3; ++c) {
-                sc3[c] = std::sqrt(local->m[0][c] * local->m[0][c] + local->m[1][c] * local->m[1][c] + local->m[2][c] * local->m[2][c]);
-            }
-            double det = local->m[0][0] * (local->m[1][1] * local->m[2][2] - local->m[1][2] * local->m[2][1]) -
-                         local->m[0][1] * (local->m[1][0] * local->m[2][2] - local->m[1][2] * local->m[2][0]) +
-                         local->m[0][2] * (local->m[1][0] * local->m[2][1] - local->m[1][1] * local->m[2][0]);
-            if (det < 0) for (int c = 0; c < 3; ++c) sc3[c] = -sc3[c];
-            for (int r = 0; r < 3; ++r) for (int c = 0; c < 3; ++c) a[r][c] = local->m[r][c] / sc3[c];
-            double tr = a[0][0] + a[1][1] + a[2][2], q[4];
-            if (tr > 0) {
-                double s = 0.5 / std::sqrt(tr + 1.0);
-                q[0] = (a[2][1] - a[1][2]) * s; q[1] = (a[0][2] - a[2][0]) * s; q[2] = (a[1][0] - a[0][1]) * s; q[3] = 0.25 / s;
+            // gltf crate 1.x `Transform::Matrix { matrix }.decomposed()` (scene/mod.rs; restated from its published source -- the crate
+            // is not vendored): ALL in f32.  i = upper 3x3 by columns; sx = |i.x|, sy = |i.y|, sz = signum(det i) * |i.z| (a mirror goes to
+            // the z scale only); columns multiplied by 1/s; rotation = Quaternion::from_matrix(i) with the cgmath branch order.
+            float x[3] = {cm[0], cm[1], cm[2]}, y[3] = {cm[4], cm[5], cm[6]}, z[3] = {cm[8], cm[9], cm[10]};
+            auto mag = [](const float* v) { return std::sqrt((v[0] * v[0] + v[1] * v[1]) + v[2] * v[2]); };
+            const float det = (x[0] * (y[1] * z[2] - z[1] * y[2]) - y[0] * (x[1] * z[2] - z[1] * x[2])) + z[0] * (x[1] * y[2] - y[1] * x[2]);
+            const float sx = mag(x), sy = mag(y), sz = std::copysign(1.0f, det) * mag(z);
+            const float ix = 1.0f / sx, iy = 1.0f / sy, iz = 1.0f / sz;
+            for (int a = 0; a < 3; ++a) { x[a] = x[a] * ix; y[a] = y[a] * iy; z[a] = z[a] * iz; }
+            const float trace = (x[0] + y[1]) + z[2];
+            float q[4];
+            if (trace >= 0.0f) {
+                float s = std::sqrt(1.0f + trace);
+                q[3] = 0.5f * s; s = 0.5f / s;
+                q[0] = (y[2] - z[1]) * s; q[1] = (z[0] - x[2]) * s; q[2] = (x[1] - y[0]) * s;
+            } else if (x[0] > y[1] && x[0] > z[2]) {
+                float s = std::sqrt(((x[0] - y[1]) - z[2]) + 1.0f);
+                q[0] = 0.5f * s; s = 0.5f / s;
+                q[1] = (y[0] + x[1]) * s; q[2] = (x[2] + z[0]) * s; q[3] = (y[2] - z[1]) * s;
+            } else if (y[1] > z[2]) {
+                float s = std::sqrt(((y[1] - x[0]) - z[2]) + 1.0f);
+                q[1] = 0.5f * s; s = 0.5f / s;
+                q[2] = (z[1] + y[2]) * s; q[0] = (y[0] + x[1]) * s; q[3] = (z[0] - x[2]) * s;
             } else {
-                int i = 0; if (a[1][1] > a[i][i]) i = 1; if (a[2][2] > a[i][i]) i = 2;
-                int j = (i + 1) % 3, k = (i + 2) % 3;
-                double s = 2.0 * std::sqrt(1.0 + a[i][i] - a[j][j] - a[k][k]);
-                q[3] = (a[k][j] - a[j][k]) / s; q[i] = 0.25 * s; q[j] = (a[j][i] + a[i][j]) / s; q[k] = (a[k][i] + a[i][k]) / s;
+                float s = std::sqrt(((z[2] - x[0]) - y[1]) + 1.0f);
+                q[2] = 0.5f * s; s = 0.5f / s;
+                q[0] = (x[2] + z[0]) * s; q[1] = (z[1] + y[2]) * s; q[3] = (x[1] - y[0]) * s;
             }
-            rot->i = (double)(float)q[0]; rot->j = (double)(float)q[1]; rot->k = (double)(float)q[2]; rot->w = (double)(float)q[3];
+            rot->i = (double)q[0]; rot->j = (double)q[1]; rot->k = (double)q[2]; rot->w = (double)q[3];
             return true;
         }
         float t[3] = {0, 0, 0}, r[4] = {0, 0, 0, 1}, s[3] = {1, 1, 1};

@@ -35,7 +35,7 @@ CONVERGED = [  # scene, W, H, spp
     ("practice3_3", 64, 64, 4096),
     ("practice3_4", 64, 64, 4096),
     ("practice3_5", 64, 64, 4096),
-    ("working", 50, 50, 1024),       # 1 379 primitives with random rotations: max_attempts 64 on both sides (see MAX_ATTEMPTS)
+    ("working", 50, 50, 16384),      # 1 379 primitives with random rotations: max_attempts 64 on both sides (see MAX_ATTEMPTS); heavy-tailed: needs the samples
 ]
 # BASELINE.json configs 1-2 at their NATIVE DIMENSIONS: stored as means over BLOCK x BLOCK pixel blocks (small fixtures)
 NATIVE_BLOCKS = [("practice3_1", 256, 4), ("practice3_5", 256, 4)]   # scene, oracle spp, block

@@ -295,3 +295,51 @@ def test_malformed_gltf_is_rejected_not_read_out_of_bounds(rt, tmp_path):
     with pytest.raises(rt.RtError) as e:                                    # 100 000 nested arrays: bounded recursion, clean error
         load("[" * 100000, "deep.gltf")
     assert e.value.code == rt.RT_ERR_FORMAT
+
+
+def test_matrix_nodes_follow_the_gltf_crate_decomposition(rt, oracle, tmp_path):
+    """ADVICE r1: `Transform::Matrix.decomposed()` of the gltf crate works in f32, gives a mirror to the z scale only
+    (sz = signum(det) |z|) and converts with the cgmath branch order of Quaternion::from_matrix.  Pure rotations about every axis by
+    angles that reach all four branches, a scaled rotation and MIRRORED matrices: the product loader equals the oracle loader bit for
+    bit, and for pure rotations the normals come out rotated by that rotation."""
+    import base64
+    import json
+    import struct
+    pos = struct.pack("<9f", 0, 0, 0, 1, 0, 0, 0, 1, 0)
+    nrm = struct.pack("<9f", 0, 0, 1, 0, 0, 1, 0, 0, 1)
+    idx = struct.pack("<3B", 0, 1, 2) + b"\0"
+    blob = pos + nrm + idx
+
+    def rot(axis, ang):
+        c, s = np.cos(ang), np.sin(ang)
+        x, y, z = axis
+        return np.array([[c + x * x * (1 - c), x * y * (1 - c) - z * s, x * z * (1 - c) + y * s],
+                         [y * x * (1 - c) + z * s, c + y * y * (1 - c), y * z * (1 - c) - x * s],
+                         [z * x * (1 - c) - y * s, z * y * (1 - c) + x * s, c + z * z * (1 - c)]])
+    cases = [("rx_30", rot((1, 0, 0), 0.5), 1), ("rx_170", rot((1, 0, 0), 2.97), 1), ("ry_170", rot((0, 1, 0), 2.97), 1), ("rz_170", rot((0, 0, 1), 2.97), 1),
+             ("scaled", rot((0.6, 0.0, 0.8), 1.1) @ np.diag([2.0, 3.0, 0.5]), 0), ("mirror", rot((0, 1, 0), 0.7) @ np.diag([1.0, 1.0, -1.0]), 0),
+             ("mirror_x", rot((0, 0, 1), 0.3) @ np.diag([-2.0, 1.0, 1.0]), 0)]
+    for name, R, pure in cases:
+        M = np.eye(4); M[:3, :3] = R; M[:3, 3] = [0.5, -1.0, 2.0]
+        g = {
+            "asset": {"version": "2.0"},
+            "buffers": [{"byteLength": len(blob), "uri": "data:application/octet-stream;base64," + base64.b64encode(blob).decode()}],
+            "bufferViews": [{"buffer": 0, "byteOffset": 0, "byteLength": 36}, {"buffer": 0, "byteOffset": 36, "byteLength": 36}, {"buffer": 0, "byteOffset": 72, "byteLength": 3}],
+            "accessors": [{"bufferView": 0, "componentType": 5126, "count": 3, "type": "VEC3"}, {"bufferView": 1, "componentType": 5126, "count": 3, "type": "VEC3"},
+                          {"bufferView": 2, "componentType": 5121, "count": 3, "type": "SCALAR"}],
+            "meshes": [{"primitives": [{"attributes": {"POSITION": 0, "NORMAL": 1}, "indices": 2}]}],
+            "cameras": [{"type": "perspective", "perspective": {"yfov": 0.5, "znear": 0.1}}],
+            "nodes": [{"mesh": 0, "matrix": [float(v) for v in M.T.reshape(-1)]}, {"camera": 0, "translation": [0, 0, 5]}],
+        }
+        path = tmp_path / f"{name}.gltf"
+        path.write_text(json.dumps(g))
+        sc = rt.Scene.from_gltf(str(path), 8, 8, 1, device=-1)
+        d = sc.desc()
+        fl = oracle.convert_gltf_to_scene(str(path), 8, 8, 1)
+        assert np.array_equal(d["tri_v"], fl.tri_v) and np.array_equal(d["tri_n"], fl.tri_n), name
+        n = d["tri_n"][0, :3]
+        assert abs(np.linalg.norm(n) - 1) < 1e-6, name
+        if pure:
+            assert np.allclose(n, R @ [0, 0, 1], atol=2e-6), (name, n, R @ [0, 0, 1])
+        assert np.allclose(d["tri_v"][0, 3:6], R @ [1, 0, 0] + [0.5, -1.0, 2.0], atol=1e-6), name     # positions always go through the full matrix
+        sc.close()

@@ -14,7 +14,7 @@ ROWS = [("practice3_1", 640, 480, 64), ("practice3_5", 512, 512, 64), ("practice
         ("practice7_2", 512, 512, 64), ("practice7_2", 1920, 1080, 64), ("practice7_3", 512, 512, 64), ("practice7_3", 1920, 1080, 64), ("practice3_3", 512, 512, 64),
         ("practice3_4", 512, 512, 64), ("working", 400, 400, 256)]
 GOLD = {"practice7_1": (64, 64, 16384), "practice7_4": (64, 64, 16384), "practice7_2": (32, 32, 4096), "practice7_3": (32, 32, 4096), "practice3_1": (80, 60, 4096),
-        "practice3_5": (64, 64, 4096), "practice3_3": (64, 64, 4096), "practice3_4": (64, 64, 4096), "working": (50, 50, 1024)}
+        "practice3_5": (64, 64, 4096), "practice3_3": (64, 64, 4096), "practice3_4": (64, 64, 4096), "working": (50, 50, 16384)}
 
 
 def scene_file(name):
