@@ -224,22 +224,9 @@ def main():
 
     def step(record=False):
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(5)] if record else None
+        multigpu.render_frame_sharded(scene, accum, rgb_dev, seed=args.seed, samples=S, rank=rank, world=world, stream_ptr=sp, resolve=resolve,
+                                      mark=(lambda k: ev[k].record(stream)) if record else None, kernel_variant=args.variant)
         if record:
-            ev[0].record(stream)
-        accum.zero_()
-        if record:
-            ev[1].record(stream)
-        if hi > lo:
-            scene.render_accumulate_device(accum.data_ptr(), sp, seed=args.seed, sample_begin=lo, sample_end=hi, kernel_variant=args.variant)
-        if record:
-            ev[2].record(stream)
-        multigpu.reduce_to_root(accum, 0)
-        if record:
-            ev[3].record(stream)
-        if rank == 0:
-            resolve(accum.data_ptr(), rgb_dev.data_ptr(), sp)
-        if record:
-            ev[4].record(stream)
             ev_pairs.append(ev)
 
     def barrier():
@@ -313,12 +300,9 @@ def main():
         if world == 1:
             sc2.render_into(rgb_host.numpy(), seed=args.seed, kernel_variant=args.variant)       # rt_render: D2H inside the call
         else:
-            accum.zero_()
-            if hi > lo:
-                sc2.render_accumulate_device(accum.data_ptr(), sp, seed=args.seed, sample_begin=lo, sample_end=hi, kernel_variant=args.variant)
-            multigpu.reduce_to_root(accum, 0)
+            multigpu.render_frame_sharded(sc2, accum, rgb_dev, seed=args.seed, samples=S, rank=rank, world=world, stream_ptr=sp, resolve=resolve,
+                                          kernel_variant=args.variant)
             if rank == 0:
-                resolve(accum.data_ptr(), rgb_dev.data_ptr(), sp)
                 rgb_host.copy_(rgb_dev, non_blocking=True)
             torch.cuda.synchronize()
         sc2.close()

@@ -25,12 +25,27 @@ def reduce_to_root(accum, root: int = 0):
     return accum
 
 
-def render_frame_sharded(scene, accum, rgb_dev, *, seed: int, samples: int, rank: int, world: int, stream_ptr: int, resolve):
-    """One frame: local shard -> reduce -> (rank 0) resolve.  accum / rgb_dev are torch CUDA tensors."""
+def render_frame_sharded(scene, accum, rgb_dev, *, seed: int, samples: int, rank: int, world: int, stream_ptr: int, resolve, mark=None, **render_kw):
+    """One frame of the sharded path: zero the accumulator -> local sample shard (rt_render_accumulate_device) -> reduce to rank 0 ->
+    (rank 0) resolve.  accum / rgb_dev are torch tensors on the rank's device (any object with zero_() / data_ptr()); `scene` needs
+    render_accumulate_device(accum_ptr, stream_ptr, **kw); `resolve(accum_ptr, rgb_ptr, stream_ptr)` is color_to_pixel on the device.
+    mark(k), if given, is called at the phase boundaries k = 0 (start), 1 (zeroed), 2 (rendered), 3 (reduced), 4 (resolved) -- bench.py
+    records CUDA events there.  This is the ONE implementation of the per-rank frame: bench.py's timed loop, its end-to-end leg and the
+    gloo test all call it."""
     lo, hi = shard_range(samples, rank, world)
+    if mark:
+        mark(0)
     accum.zero_()
+    if mark:
+        mark(1)
     if hi > lo:
-        scene.render_accumulate_device(accum.data_ptr(), stream_ptr, seed=seed, sample_begin=lo, sample_end=hi)
+        scene.render_accumulate_device(accum.data_ptr(), stream_ptr, seed=seed, sample_begin=lo, sample_end=hi, **render_kw)
+    if mark:
+        mark(2)
     reduce_to_root(accum, 0)
+    if mark:
+        mark(3)
     if rank == 0:
         resolve(accum.data_ptr(), rgb_dev.data_ptr(), stream_ptr)
+    if mark:
+        mark(4)

@@ -39,7 +39,24 @@ if rank == 0:
     full = per_sample.sum(0)
     assert torch.allclose(acc[:, :3], full, rtol=1e-6, atol=1e-6), "reduce != sum of shards"
     assert torch.all(acc[:, 3] == S)
+# the whole per-rank frame (the function bench.py times) with a stand-in scene that "renders" the shard on the CPU
+class FakeScene:
+    def render_accumulate_device(self, accum_ptr, stream_ptr, seed=0, sample_begin=0, sample_end=0, **kw):
+        assert accum_ptr == acc2.data_ptr() and kw == {"kernel_variant": 7}
+        acc2[:, :3] += per_sample[sample_begin:sample_end].sum(0); acc2[:, 3] += sample_end - sample_begin
+acc2 = torch.full((H * W, 4), 99.0)                                              # stale contents: the frame must zero them
+rgb = torch.zeros(H * W, 3)
+marks = []
+def resolve(a_ptr, r_ptr, s_ptr):
+    assert a_ptr == acc2.data_ptr() and r_ptr == rgb.data_ptr()
+    rgb[:] = acc2[:, :3] / acc2[:, 3:4]
+multigpu.render_frame_sharded(FakeScene(), acc2, rgb, seed=1, samples=S, rank=rank, world=2, stream_ptr=0, resolve=resolve, mark=marks.append, kernel_variant=7)
+assert marks == [0, 1, 2, 3, 4]
+if rank == 0:
+    assert torch.allclose(rgb, per_sample.mean(0), rtol=1e-5, atol=1e-6) and torch.all(acc2[:, 3] == S)
     print("OK")
+else:
+    assert not rgb.any()                                                         # only the root resolves
 dist.barrier()
 dist.destroy_process_group()
 '''
