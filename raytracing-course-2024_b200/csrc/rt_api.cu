@@ -462,10 +462,10 @@ void cache_put(void* p, size_t bytes) {
         std::lock_guard<std::mutex> lock(cache_mutex());
         std::vector<CachedBlock>& c = cache_blocks();
         c.push_back({dev, p, bytes});
-        if (c.size() > kCacheSlots) {
-            size_t k = 0;
-            for (size_t i = 1; i < c.size(); ++i) if (c[i].bytes < c[k].bytes) k = i;
-            if (c[k].device == dev) { evict = c[k].p; c.erase(c.begin() + (long)k); }     // (another device's block stays: freeing needs that device current)
+        if (c.size() > kCacheSlots) {                        // over capacity: release the smallest block of THIS device (freeing needs it current;
+            long k = -1;                                     // the block just pushed belongs to it, so one always exists)
+            for (size_t i = 0; i < c.size(); ++i) if (c[i].device == dev && (k < 0 || c[i].bytes < c[(size_t)k].bytes)) k = (long)i;
+            if (k >= 0) { evict = c[(size_t)k].p; c.erase(c.begin() + k); }
         }
     }
     if (evict) cudaFree(evict);
@@ -489,7 +489,12 @@ void* cache_take(size_t need, size_t* got) {
 template <class T>
 int ensure(T** p, size_t* cap, size_t need_elems) {
     if (*cap >= need_elems && *p) return RT_OK;
-    if (*p) cache_put(*p, *cap * sizeof(T));
+    if (*p) {
+        // the old block may still be read by work queued on ANY stream of this device (rt_render_accumulate_device is asynchronous and
+        // runs on the caller's stream): wait like the implicit synchronisation of cudaFree did before the block can change owner
+        cudaDeviceSynchronize();
+        cache_put(*p, *cap * sizeof(T));
+    }
     *p = nullptr; *cap = 0;
     size_t got = 0;
     if (void* c = cache_take(need_elems * sizeof(T), &got)) { *p = (T*)c; *cap = got / sizeof(T); return RT_OK; }
@@ -795,7 +800,7 @@ int rt_release_device_cache(void) {
 void rt_scene_destroy(RtScene* s) {
     if (!s) return;
     if (s->stream || s->blob_dev) cudaSetDevice(s->device);
-    if (s->stream) cudaStreamSynchronize(s->stream);          // the frame buffers go back to the cache: nothing may still be writing them
+    if (s->stream || s->blob_dev) cudaDeviceSynchronize();    // the frame buffers go back to the cache: nothing (on any stream) may still use them
     cache_put(s->layers, s->layers_cap * sizeof(float4)); cache_put(s->accum, s->accum_cap * sizeof(float4));
     cache_put(s->rgb_dev, s->rgb_cap); cache_put(s->lin_dev, s->lin_cap * sizeof(float));
     cudaFree(s->blob_dev); cudaFree(s->tri_d_dev);

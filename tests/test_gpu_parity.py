@@ -724,3 +724,29 @@ def test_automatic_scene_placement_keeps_two_blocks_per_sm(gpu_rt, oracle):
     d = np.abs(auto.astype(np.float64) - forced)
     assert np.median(d) <= 1e-5 * np.abs(auto).mean() and d.mean() <= 2e-2 * np.abs(auto).mean()
     sc.close()
+
+
+def test_frame_buffer_cache_is_transparent_and_bounded(gpu_rt):
+    """rt_scene_destroy parks the big frame buffers for the next scene (include/rt_api.h, rt_release_device_cache): renders must not
+    depend on what a recycled buffer held (other frame size, other scene, tile shards, ray_depth 0), and repeated create / render /
+    destroy cycles must not grow the device memory in use."""
+    import torch
+    ref = {}
+    for name, W, H, spp in (("practice7_4", 640, 360, 8), ("practice7_1", 512, 512, 4)):
+        sc = gpu_rt.Scene.from_gltf(scene_path(name), W, H, spp)
+        ref[name] = sc.render(seed=3)[0].copy()
+        sc.close()
+    gpu_rt.release_device_cache()
+    free0 = torch.cuda.mem_get_info()[0]
+    for k in range(12):
+        name, W, H, spp = (("practice7_4", 640, 360, 8), ("practice7_1", 512, 512, 4))[k % 2]
+        sc = gpu_rt.Scene.from_gltf(scene_path(name), W, H, spp)
+        if k % 3 == 0:
+            sc.render_linear(seed=9, tile_shard=(0, 2))                  # leaves zeros / partial data in the recycled layers
+        img, _ = sc.render(seed=3)
+        assert np.array_equal(img, ref[name]), (k, name)
+        sc.close()
+    used_cached = free0 - torch.cuda.mem_get_info()[0]
+    assert used_cached < 400e6, used_cached                                # at most the parked blocks of two small frames
+    gpu_rt.release_device_cache()
+    assert free0 - torch.cuda.mem_get_info()[0] < 64e6
