@@ -750,3 +750,23 @@ def test_frame_buffer_cache_is_transparent_and_bounded(gpu_rt):
     assert used_cached < 400e6, used_cached                                # at most the parked blocks of two small frames
     gpu_rt.release_device_cache()
     assert free0 - torch.cuda.mem_get_info()[0] < 64e6
+
+
+def test_reference_own_test_vndf_on_the_device(gpu_rt):
+    """`tests::test_vndf` (tests.rs:43-49, the only live test of the reference for this path) evaluated with the DEVICE pdf: n = z,
+    v = normalize(z + z) = z, roughness 0.04, 1e6 uniform directions, `(avg * 4 pi - 1) < 0.05` as written (one-sided) -- and the
+    two-sided version of the same integral with an integrator that resolves the alpha = 0.0016 lobe."""
+    rng = np.random.default_rng(4349)
+    cnt = 1_000_000
+    z = np.array([0.0, 0.0, 1.0], dtype=np.float32)
+    N = np.tile(z, (cnt, 1)); V = np.tile(z, (cnt, 1)); R = np.full((cnt, 1), 0.04, dtype=np.float32)
+    l = rng.normal(size=(cnt, 3)); l /= np.linalg.norm(l, axis=1, keepdims=True)
+    pdf = gpu_rt.eval_fn(gpu_rt.FN_PDF_VNDF, np.concatenate([N, l.astype(np.float32), V, R], axis=1))[:, 0].astype(np.float64)
+    avg = np.where(np.isfinite(pdf), pdf, 0.0).mean()
+    assert (avg * 4 * np.pi - 1.0) < 0.05
+    l2, inv_q = _log_polar_directions(np.array([0.0, 0.0, 1.0]), cnt, rng, theta_min=1e-7)
+    l32 = np.ascontiguousarray(l2, dtype=np.float32)
+    p2 = gpu_rt.eval_fn(gpu_rt.FN_PDF_VNDF, np.concatenate([N, l32, V, R], axis=1))[:, 0].astype(np.float64)
+    above = (l32.astype(np.float64) + z) @ z > 0
+    w = np.where(above & np.isfinite(p2), p2, 0.0) * inv_q
+    assert abs(w.mean() - 1.0) < max(5 * w.std() / np.sqrt(cnt), 0.01), w.mean()
