@@ -1,6 +1,6 @@
 """Quick GPU check of the general-primitive path against the oracle (development aid; the real gates are tests/test_gpu_general.py)."""
 import os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import numpy as np
 import oracle as O

@@ -5,7 +5,7 @@ roofline fraction (same constants as bench.py), primary-hit parity against the o
 oracle render exists (tests/golden), the mean-luminance difference of a GPU render at that size.  One JSON line per row."""
 import json, os, sys, time
 import numpy as np
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 sys.path.insert(0, ROOT)
 import oracle as O          # noqa: E402  (test infrastructure: CPU column and parity checks only)
 import rtb200 as rt         # noqa: E402

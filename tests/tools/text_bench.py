@@ -1,7 +1,7 @@
 """Throughput of the general-primitive path on the text scenes at their native DIMENSIONS (BASELINE.json configs 1-2) and of the
 oracle on the same frames (bounded rows) -- numbers for BASELINE.md.  python tools/text_bench.py [spp]"""
 import json, os, sys, time
-ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__))); sys.path.insert(0, ROOT)
+ROOT = os.path.dirname(os.path.dirname(os.path.dirname(os.path.abspath(__file__)))); sys.path.insert(0, ROOT)
 import numpy as np
 import oracle as O
 import rtb200 as rt

@@ -11,5 +11,5 @@ CMD='ncu --metrics dram__bytes_read.sum,dram__bytes_write.sum,gpu__time_duration
 $CMD > gpurun_out/traffic_run.log 2>&1; echo "ncu traffic rc=$?"
 python tools/ncu_traffic.py gpurun_out/traffic.csv gpurun_out/r2_bench_traffic.json "$CMD" | cut -c1-400
 python tools/spp_fit.py > gpurun_out/r2_spp_fit.txt 2>&1; tail -1 gpurun_out/r2_spp_fit.txt
-python tools/text_bench.py > gpurun_out/r2_text_scenes.jsonl 2>&1; echo "text bench rc=$?"
-python tools/results_table.py > gpurun_out/r2_results_table.jsonl 2>&1; echo "results table rc=$?"; cut -c1-260 gpurun_out/r2_results_table.jsonl
+python tests/tools/text_bench.py > gpurun_out/r2_text_scenes.jsonl 2>&1; echo "text bench rc=$?"
+python tests/tools/results_table.py > gpurun_out/r2_results_table.jsonl 2>&1; echo "results table rc=$?"; cut -c1-260 gpurun_out/r2_results_table.jsonl
