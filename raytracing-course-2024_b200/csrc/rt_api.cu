@@ -581,7 +581,7 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     // through L1 / L2 -- two warps fewer per SM bring the blocks under 97 KB of shared memory each, which lets the driver pick the
     // 196 KB carve-out instead of 228 KB: 60 KB of L1 instead of 28 KB (measured: practice7_2 +4 %, practice7_3 +7 %)
     const int cfg_env = env_int("RT_WAVE_CFG", -1);
-    const int cfg_smem = cfg_env >= 0 ? cfg_env : 2, cfg_gmem = cfg_env >= 0 ? cfg_env : 5;
+    const int cfg_smem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : 2), cfg_gmem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : 5);
     // sample chunks: enough (pixel, chunk) items to keep every resident path slot busy many times over
     int lanes = 0;
     if (plan->use_smem && placement == 0) {

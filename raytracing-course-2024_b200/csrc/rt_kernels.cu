@@ -313,7 +313,7 @@ static cudaError_t launch_render_t(const RenderArgs& a, int device_sms, cudaStre
 
 // variant: 1 = v1 per-lane megakernel, 2 = v3 warp-local wavefront with while-while bursts, 3 = v3 with phased bursts.
 // cfg (v3 only): resident-thread configuration, see wave_cfg_name().  General-primitive scenes (a.L.general) run on the phased
-// wavefront kernel only, 256 threads x 2 blocks per SM (the wider vertex code wants more than the 80 registers of 384 x 2).
+// wavefront kernel only, 320 threads x 2 blocks per SM (the wider vertex code wants more than the 80 registers of 384 x 2; cfg 0 = 256 x 2).
 static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int sms, cudaStream_t s, KernelInfo* info, bool launch, int* lanes) {
 #define RT_DISPATCH(FN, ...)                                                                                                   \
     (use_smem ? (stats ? FN<SmemSpace, true __VA_ARGS__>(a, sms, s, info, launch, lanes) : FN<SmemSpace, false __VA_ARGS__>(a, sms, s, info, launch, lanes)) \
@@ -330,7 +330,8 @@ static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bo
     }
     if (a.L.general) {
         if (variant != 3) return cudaErrorInvalidValue;
-        return RT_DISPATCH(launch_wave_t, , 1, 256, 2, true);
+        if (cfg == 0) return RT_DISPATCH(launch_wave_t, , 1, 256, 2, true);
+        return RT_DISPATCH(launch_wave_t, , 1, 320, 2, true);      // measured: 320 x 2 (95 registers, no spills) beats 256 / 288 / 352 / 384 x 2 by 4-11 % on the text scenes
     }
     if (variant == 1) return RT_DISPATCH(launch_render_t);
     if (variant == 3) { RT_WAVE(1) }
