@@ -76,8 +76,8 @@ namespace {
 
 struct BlobWriter {
     std::vector<char>& buf;
-    uint32_t add(const void* data, size_t bytes) {
-        size_t off = (buf.size() + 15u) & ~(size_t)15u;
+    uint32_t add(const void* data, size_t bytes, size_t align = 16) {
+        size_t off = (buf.size() + (align - 1)) & ~(align - 1);
         buf.resize(off + ((bytes + 15u) & ~(size_t)15u), 0);
         if (bytes) std::memcpy(buf.data() + off, data, bytes);
         return (uint32_t)off;
@@ -149,6 +149,58 @@ std::vector<float> octant_nodes(const rtb::FlatBvh& b, size_t stride_bytes) {
         for (int c = 0; c < 2; ++c) {      // inner children as byte offsets (index * RT_NODE_BYTES), leaf codes unchanged
             const int32_t r = b.child[(size_t)n * 2 + (size_t)c];
             o[24 + c] = i2f(r >= 0 ? r * (int32_t)stride_bytes : r);
+        }
+    }
+    return out;
+}
+
+// FlatBvh -> quantised 32-byte pair nodes (rt_device.cuh pair_step_quant).  Grid: 16 bits per axis over the union of the finite
+// child boxes, the scene box mapped to [2, 65533]; a minimum is moved down and a maximum up until the plane the DEVICE reconstructs
+// (qorg + q * qcell, evaluated here with the same float constants) lies at least 1.5 cells outside the true plane -- the slack
+// that absorbs the FP32 rounding of fma(q, qcell / d, -(o - qorg) / d) for ray origins within ~100 scene diameters.
+std::vector<uint32_t> quant_nodes(const rtb::FlatBvh& b, float* qorg, float* qcell) {
+    double lo[3] = {1e300, 1e300, 1e300}, hi[3] = {-1e300, -1e300, -1e300};
+    auto slot_box = [&b](int node, int s, float* mn, float* mx) {
+        const float* A = &b.box_a[(size_t)node * 4]; const float* B = &b.box_b[(size_t)node * 4]; const float* C = &b.box_c[(size_t)node * 4];
+        const float* xy = s == 0 ? A : B;
+        mn[0] = xy[0]; mx[0] = xy[1]; mn[1] = xy[2]; mx[1] = xy[3]; mn[2] = C[s * 2]; mx[2] = C[s * 2 + 1];
+    };
+    for (int n = 0; n < b.n_nodes; ++n)
+        for (int s = 0; s < 2; ++s) {
+            float mn[3], mx[3];
+            slot_box(n, s, mn, mx);
+            if (mn[0] > 1e29f) continue;                       // the far-away filler of a one-leaf tree
+            for (int a = 0; a < 3; ++a) { lo[a] = std::min(lo[a], (double)mn[a]); hi[a] = std::max(hi[a], (double)mx[a]); }
+        }
+    for (int a = 0; a < 3; ++a) {
+        if (lo[a] > hi[a]) { lo[a] = 0.0; hi[a] = 0.0; }
+        qcell[a] = (float)std::max((hi[a] - lo[a]) / 65531.0, 1e-12);
+        qorg[a] = (float)(lo[a] - 2.0 * (double)qcell[a]);
+    }
+    auto q_of = [&](int a, double p, bool lower) -> uint32_t {
+        const double cell = (double)qcell[a], org = (double)qorg[a];
+        double q = lower ? std::floor((p - org) / cell) - 2.0 : std::ceil((p - org) / cell) + 2.0;
+        q = std::min(std::max(q, 0.0), 65535.0);
+        if (lower) while (q > 0.0 && org + q * cell > p - 1.5 * cell) q -= 1.0;
+        else while (q < 65535.0 && org + q * cell < p + 1.5 * cell) q += 1.0;
+        return (uint32_t)q;
+    };
+    std::vector<uint32_t> out((size_t)std::max(b.n_nodes, 1) * 8, 0u);
+    for (int n = 0; n < b.n_nodes; ++n) {
+        uint32_t* o = &out[(size_t)n * 8];
+        uint32_t qmn[2][3], qmx[2][3];
+        for (int s = 0; s < 2; ++s) {
+            float mn[3], mx[3];
+            slot_box(n, s, mn, mx);
+            for (int a = 0; a < 3; ++a) {
+                if (mn[0] > 1e29f) { qmn[s][a] = 65535u; qmx[s][a] = 65535u; }      // filler: a point at the far corner
+                else { qmn[s][a] = q_of(a, (double)mn[a], true); qmx[s][a] = q_of(a, (double)mx[a], false); }
+            }
+        }
+        for (int a = 0; a < 3; ++a) { o[a * 2] = qmn[0][a] | (qmn[1][a] << 16); o[a * 2 + 1] = qmx[0][a] | (qmx[1][a] << 16); }
+        for (int c = 0; c < 2; ++c) {
+            const int32_t r = b.child[(size_t)n * 2 + (size_t)c];
+            o[6 + c] = (uint32_t)(r >= 0 ? r * 32 : r);
         }
     }
     return out;
@@ -390,6 +442,20 @@ int flatten_scene(RtScene* s) {
         const std::vector<float> lnodes = octant_nodes(s->light_bvh, RT_NODE_BYTES);
         L.lnodes = w.add(lnodes.data(), lnodes.size() * 4);
     }
+    // entry 0 = RT_CUR_DONE, one marker per walk; the light-pdf walk runs on top of a ray's live stack (wavefront kernel)
+    const int light_extra = use_light_bvh ? s->light_bvh.depth + 2 : 0;
+    const int need = s->bvh.depth + 3 + light_extra;
+    if (need <= 96) s->stack_entries = (uint32_t)std::max(8, (need + 3) / 4 * 4);
+    else return fail(RT_ERR_LIMIT, "BVH depth " + std::to_string(s->bvh.depth) + " exceeds the traversal stack");
+    // global-memory triangle scenes: quantised 32-byte nodes for the nearest-hit walk of the render kernel (the octant-ordered pair
+    // nodes stay for the f64 parity walk, the per-lane kernel and forced placements)
+    const bool too_big_for_smem = !refs_packable(s->bvh) || s->blob_host.size() > (size_t)env_int("RT_SMEM_SCENE_MAX_BYTES", 48 * 1024);
+    const int node_format = env_int("RT_NODE_FORMAT", 2);       // 0: octant-ordered pair nodes only, 2: + quantised 32-byte pair nodes (A/B knob)
+    if (too_big_for_smem && !gen && node_format == 2 && (uint64_t)s->bvh.n_nodes * 32u <= 0x7fffffffull) {
+        const std::vector<uint32_t> qn = quant_nodes(s->bvh, L.qorg, L.qcell);
+        L.qnodes = w.add(qn.data(), qn.size() * 4, 32);
+        L.quant = 1;
+    }
     if (s->blob_host.size() > 0xffffffffull || (uint64_t)std::max(s->bvh.n_nodes, s->light_bvh.n_nodes) * 128u > 0x7fffffffull)
         return fail(RT_ERR_LIMIT, "scene exceeds the 4 GiB device blob / 2 GiB node array addressed by 32-bit offsets");
     L.total_bytes = (uint32_t)s->blob_host.size();
@@ -399,10 +465,6 @@ int flatten_scene(RtScene* s) {
     L.inv_n_lights = n_lights > 0 ? 1.0f / (float)n_lights : 0.0f;
     L.general = gen ? 1 : 0; L.n_planes = n_planes; L.has_dielectric = has_dielectric ? 1 : 0;
 
-    // entry 0 = RT_CUR_DONE, one marker per walk; the light-pdf walk runs on top of a ray's live stack (wavefront kernel)
-    const int need = s->bvh.depth + 3 + (use_light_bvh ? s->light_bvh.depth + 2 : 0);
-    if (need <= 96) s->stack_entries = (uint32_t)std::max(8, (need + 3) / 4 * 4);
-    else return fail(RT_ERR_LIMIT, "BVH depth " + std::to_string(s->bvh.depth) + " exceeds the traversal stack");
     const int smem_limit = env_int("RT_SMEM_SCENE_MAX_BYTES", 48 * 1024);
     L.packed_refs = refs_packable(s->bvh) ? 1 : 0;
     s->use_smem = (int)L.total_bytes <= smem_limit && L.packed_refs;   // the shared-memory kernel reads packed references
@@ -581,20 +643,20 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     // through L1 / L2 -- two warps fewer per SM bring the blocks under 97 KB of shared memory each, which lets the driver pick the
     // 196 KB carve-out instead of 228 KB: 60 KB of L1 instead of 28 KB (measured: practice7_2 +4 %, practice7_3 +7 %)
     const int cfg_env = env_int("RT_WAVE_CFG", -1);
-    const int cfg_smem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : 2), cfg_gmem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : 5);
+    const int cfg_smem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : 2), cfg_gmem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : (s->L.quant ? 2 : 5));   // quantised walk: 384 x 2 again (the L1 is no longer the limit: +4 % over 352 x 2)
     // sample chunks: enough (pixel, chunk) items to keep every resident path slot busy many times over
     int lanes = 0;
     if (plan->use_smem && placement == 0) {
         // automatic placement: staging the scene must not cost occupancy (a mid-size blob can push the block past half of the
         // SM's shared memory: one block per SM instead of two) -- fall back to the global-memory path in that case
         int with_smem = 0, without = 0;
-        cudaError_t es = rtd::render_resident_lanes(plan->variant, cfg_smem, true, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
+        cudaError_t es = rtd::render_resident_lanes(plan->variant, cfg_smem, true, plan->stats, s->L.general != 0, s->L.quant ? 2 : 0, s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
         if (es != cudaSuccess) { cudaGetLastError(); with_smem = 0; }
-        CUDA_TRY(rtd::render_resident_lanes(plan->variant, cfg_gmem, false, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &without));
+        CUDA_TRY(rtd::render_resident_lanes(plan->variant, cfg_gmem, false, plan->stats, s->L.general != 0, s->L.quant ? 2 : 0, s->L.total_bytes, s->stack_entries, s->sms, &without));
         if (with_smem < without * 9 / 10) { plan->use_smem = false; a.blob = s->blob_dev; }     // (352 x 2 keeps 8 % fewer lanes than 384 x 2: not a reason to leave shared memory)
     }
     plan->cfg = plan->use_smem ? cfg_smem : cfg_gmem;
-    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.general != 0, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
+    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.general != 0, s->L.quant ? 2 : 0, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
     const int n_samp = s1 - s0;
     // measured (B200): work items ~32x the resident path slots keep the end-of-frame tail short (512x512x1024 spp: +16 % over
     // 4x); frames with plenty of pixels still get up to 4 chunks of >= 128 samples (3840x2160x1024: +0.7 %)

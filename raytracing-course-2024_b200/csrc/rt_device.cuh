@@ -90,6 +90,10 @@ struct SceneLayout {
     uint32_t mat2;                               // per material: ior, material kind (as int bits), 0, 0
     int32_t n_planes;
     int32_t has_dielectric;                      // any material of kind RT_MAT_DIELECTRIC
+    // ---- quantised 32-byte pair nodes for the global-memory walks (pair_step_quant): `quant` = 1
+    uint32_t qnodes;                             // 32-byte aligned
+    int32_t quant;
+    float qorg[3], qcell[3];                     // plane = qorg + q * qcell
 };
 #define RT_BRUTE_LIGHTS 8
 
@@ -123,6 +127,13 @@ struct GmemSpace {
     RT_DEV int2 ld2i(uint32_t off) const {
         RT_BOUNDS((off & 7u) == 0u && off + 8u <= limit, RT_BOUNDS_BLOB);
         return __ldg(reinterpret_cast<const int2*>(base + off));
+    }
+    // One 32-byte sector with ONE instruction (LDG.E.256, sm_100).  The L1 data pipe spends a cycle per (lane, sector) on the
+    // scattered loads of a traversal whatever their width: 32 bytes per cycle instead of the 16 of LDG.128.
+    RT_DEV void ld8(uint32_t off, float4& a, float4& b) const {
+        RT_BOUNDS((off & 31u) == 0u && off + 32u <= limit, RT_BOUNDS_BLOB);
+        asm("ld.global.nc.v8.f32 {%0,%1,%2,%3,%4,%5,%6,%7}, [%8];"
+            : "=f"(a.x), "=f"(a.y), "=f"(a.z), "=f"(a.w), "=f"(b.x), "=f"(b.y), "=f"(b.z), "=f"(b.w) : "l"(base + off));
     }
 };
 
@@ -194,6 +205,34 @@ RT_DEV RaySetup ray_setup(float3 o, float3 d, uint32_t nodes) {
 RT_DEV float max3f(float a, float b, float c) { float r; asm("max.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 RT_DEV float min3f(float a, float b, float c) { float r; asm("min.f32 %0, %1, %2, %3;" : "=f"(r) : "f"(a), "f"(b), "f"(c)); return r; }
 
+// Child selection of a box-pair step, written in PTX so that it stays in predicate registers (nvcc turns the bool algebra into
+// integer SEL / LOP3 / PRMT chains otherwise): enter the nearer hit child (pushing the other one), or pop.
+template <bool ORDERED>
+RT_DEV void pair_descend(float t0, float t1, float e0, float e1, int2 ch, int& cur, SmemStack& st) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred h0, h1, sf, both, any;\n\t"
+        ".reg .b32 first, second;\n\t"
+        "setp.le.f32 h0, %2, %4;\n\t"
+        "setp.le.f32 h1, %3, %5;\n\t"
+        "setp.lt.f32 sf, %3, %9;\n\t"                // second child first iff it is strictly nearer (ordered walks only) ...
+        "not.pred both, h0;\n\t"
+        "or.pred sf, sf, both;\n\t"                  // ... or the first child is not hit at all
+        "and.pred sf, sf, h1;\n\t"
+        "and.pred both, h0, h1;\n\t"
+        "or.pred any, h0, h1;\n\t"
+        "selp.b32 first, %7, %6, sf;\n\t"
+        "selp.b32 second, %6, %7, sf;\n\t"
+        "@both st.shared.b32 [%1], second;\n\t"
+        "@both add.u32 %1, %1, %8;\n\t"
+        "@any mov.b32 %0, first;\n\t"
+        "@!any sub.u32 %1, %1, %8;\n\t"
+        "@!any ld.shared.b32 %0, [%1];\n\t"
+        "}"
+        : "+r"(cur), "+r"(st.top)
+        : "f"(t0), "f"(t1), "f"(e0), "f"(e1), "r"(ch.x), "r"(ch.y), "r"(st.stride), "f"(ORDERED ? t0 : t1));
+}
+
 // One box-pair step of the near-child-first traversal (interesect_with_bvh_nearest_point, bvh.rs:231-297, iterative):
 // conservative slab test of the two child boxes of node `cur`, then descend into the nearer hit child (pushing the
 // other one), or pop.  Accept/prune rule of get_aabb_intersection + bvh.rs:258-263: a box is entered iff the ray's
@@ -220,31 +259,53 @@ RT_DEV void pair_step(const Space& sp, uint32_t nodes, const RaySetup& r, float 
     const float nz0 = fmaf(Z.x, r.inv.z, -r.od.z), nz1 = fmaf(Z.y, r.inv.z, -r.od.z), fz0 = fmaf(Z.z, r.inv.z, -r.od.z), fz1 = fmaf(Z.w, r.inv.z, -r.od.z);
     const float t0 = fmaxf(max3f(nx0, ny0, nz0), 0.0f), e0 = fminf(min3f(fx0, fy0, fz0), t_best);
     const float t1 = fmaxf(max3f(nx1, ny1, nz1), 0.0f), e1 = fminf(min3f(fx1, fy1, fz1), t_best);
-    asm volatile(
-        "{\n\t"
-        ".reg .pred h0, h1, sf, both, any;\n\t"
-        ".reg .b32 first, second;\n\t"
-        "setp.le.f32 h0, %2, %4;\n\t"
-        "setp.le.f32 h1, %3, %5;\n\t"
-        "setp.lt.f32 sf, %3, %9;\n\t"                // second child first iff it is strictly nearer (ordered walks only) ...
-        "not.pred both, h0;\n\t"
-        "or.pred sf, sf, both;\n\t"                  // ... or the first child is not hit at all
-        "and.pred sf, sf, h1;\n\t"
-        "and.pred both, h0, h1;\n\t"
-        "or.pred any, h0, h1;\n\t"
-        "selp.b32 first, %7, %6, sf;\n\t"
-        "selp.b32 second, %6, %7, sf;\n\t"
-        "@both st.shared.b32 [%1], second;\n\t"
-        "@both add.u32 %1, %1, %8;\n\t"
-        "@any mov.b32 %0, first;\n\t"
-        "@!any sub.u32 %1, %1, %8;\n\t"
-        "@!any ld.shared.b32 %0, [%1];\n\t"
-        "}"
-        : "+r"(cur), "+r"(st.top)
-        : "f"(t0), "f"(t1), "f"(e0), "f"(e1), "r"(ch.x), "r"(ch.y), "r"(st.stride), "f"(ORDERED ? t0 : t1));
+    pair_descend<ORDERED>(t0, t1, e0, e1, ch, cur, st);
 #ifdef RT_DEBUG_BOUNDS
     RT_BOUNDS(st.top >= st.lo && st.top <= st.hi, RT_BOUNDS_STACK);      // (== lo: the sentinel was popped, the walk is over)
 #endif
+}
+
+// QUANTISED child-pair node for the global-memory walks: 32 bytes = ONE sector, read with one LDG.E.256.  The twelve box planes are
+// 16-bit coordinates on a global grid over the scene box (SceneLayout::qorg / qcell; minima rounded down, maxima up, two cells of
+// slack for the FP32 evaluation), the two child references stay 32-bit (inner: byte offset = index * 32):
+//   word 0 / 1: x minima / maxima (child 0 in the low half, child 1 in the high half), 2 / 3: y, 4 / 5: z, 6 / 7: references.
+// Why: the large meshes are bound by the L1 data pipe (ncu: l1tex__data_pipe_lsu_wavefronts 90-93 % of peak) and a scattered load
+// costs about one wavefront per lane and INSTRUCTION (microbenchmark tests/tools/microbench/l1_gather.cu): the octant-ordered
+// 112-byte node needs four loads per step, this one needs one, and the node array shrinks 3.5x (L1 / L2 hit rates).
+// The ray carries s = qcell / d and b = (o - qorg) / d per axis (RaySetup::inv / od), so a plane distance is fma(q, s, -b).
+#define RT_QNODE_BYTES 32u
+template <bool ORDERED = true>
+RT_DEV void pair_step_quant(const GmemSpace& sp, uint32_t qnodes, const RaySetup& r, float t_best, int& cur, SmemStack& st) {
+    float4 A, B;
+    sp.ld8(qnodes + (uint32_t)cur, A, B);
+    const bool sx = r.inv.x < 0.0f, sy = r.inv.y < 0.0f, sz = r.inv.z < 0.0f;
+    const uint32_t xn = __float_as_uint(sx ? A.y : A.x), xf = __float_as_uint(sx ? A.x : A.y);
+    const uint32_t yn = __float_as_uint(sy ? A.w : A.z), yf = __float_as_uint(sy ? A.z : A.w);
+    const uint32_t zn = __float_as_uint(sz ? B.y : B.x), zf = __float_as_uint(sz ? B.x : B.y);
+    const float nx0 = fmaf((float)(xn & 0xffffu), r.inv.x, -r.od.x), nx1 = fmaf((float)(xn >> 16), r.inv.x, -r.od.x);
+    const float fx0 = fmaf((float)(xf & 0xffffu), r.inv.x, -r.od.x), fx1 = fmaf((float)(xf >> 16), r.inv.x, -r.od.x);
+    const float ny0 = fmaf((float)(yn & 0xffffu), r.inv.y, -r.od.y), ny1 = fmaf((float)(yn >> 16), r.inv.y, -r.od.y);
+    const float fy0 = fmaf((float)(yf & 0xffffu), r.inv.y, -r.od.y), fy1 = fmaf((float)(yf >> 16), r.inv.y, -r.od.y);
+    const float nz0 = fmaf((float)(zn & 0xffffu), r.inv.z, -r.od.z), nz1 = fmaf((float)(zn >> 16), r.inv.z, -r.od.z);
+    const float fz0 = fmaf((float)(zf & 0xffffu), r.inv.z, -r.od.z), fz1 = fmaf((float)(zf >> 16), r.inv.z, -r.od.z);
+    const float t0 = fmaxf(max3f(nx0, ny0, nz0), 0.0f), e0 = fminf(min3f(fx0, fy0, fz0), t_best);
+    const float t1 = fmaxf(max3f(nx1, ny1, nz1), 0.0f), e1 = fminf(min3f(fx1, fy1, fz1), t_best);
+    pair_descend<ORDERED>(t0, t1, e0, e1, make_int2(__float_as_int(B.z), __float_as_int(B.w)), cur, st);
+#ifdef RT_DEBUG_BOUNDS
+    RT_BOUNDS(st.top >= st.lo && st.top <= st.hi, RT_BOUNDS_STACK);
+#endif
+}
+// Ray set-up for the quantised walk, and the way back to (origin, direction) at a leaf (the wavefront kernel keeps only RaySetup).
+RT_DEV RaySetup ray_setup_quant(float3 o, float3 inv_d, const float* qorg, const float* qcell) {
+    RaySetup r;
+    r.inv = f3(qcell[0] * inv_d.x, qcell[1] * inv_d.y, qcell[2] * inv_d.z);
+    r.od = f3((o.x - qorg[0]) * inv_d.x, (o.y - qorg[1]) * inv_d.y, (o.z - qorg[2]) * inv_d.z);
+    r.ox = r.oy = r.oz = 0u;
+    return r;
+}
+RT_DEV void ray_from_quant(const RaySetup& r, const float* qorg, const float* qcell, float3& o, float3& d) {
+    d = f3(qcell[0] * fast_rcp(r.inv.x), qcell[1] * fast_rcp(r.inv.y), qcell[2] * fast_rcp(r.inv.z));
+    o = f3(fmaf(r.od.x, d.x, qorg[0]), fmaf(r.od.y, d.y, qorg[1]), fmaf(r.od.z, d.z, qorg[2]));
 }
 
 // Two-sided ray/triangle test with inclusive edges: u >= 0, v >= 0, u + v <= 1, t > 0 (geometry.rs:109-113).  The
@@ -284,15 +345,16 @@ struct Hit { float t, u, v; int tri; };
 // skip_tri: triangle (BVH order) to ignore, or -1 -- used to make the reference's `t - EPS` origin back-off
 // (rendering.rs:98) robust in FP32: a ray that LEAVES the side of the surface it started on cannot hit the
 // triangle it started from in exact arithmetic, so that triangle is skipped instead of relying on a 1e-5 gap.
-template <class Space, bool STATS>
+template <class Space, bool STATS, int NODES = 0>
 RT_DEV void trace_nearest(const Space& sp, const SceneLayout& L, SmemStack& st, float3 o, float3 d, int skip_tri, Hit& hit, Counters& cnt) {
-    const RaySetup r = ray_setup(o, d, L.nodes);
+    const RaySetup r = NODES == 2 ? ray_setup_quant(o, safe_inv_dir(d), L.qorg, L.qcell) : ray_setup(o, d, L.nodes);
     hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
     st.push(RT_CUR_DONE);                        // marker: the walk may start on top of a live stack
     int cur = 0;
     for (;;) {
         while (cur >= 0) {
-            pair_step(sp, L.nodes, r, hit.t, cur, st);
+            if constexpr (NODES == 2) pair_step_quant(sp, L.qnodes, r, hit.t, cur, st);
+            else pair_step(sp, L.nodes, r, hit.t, cur, st);
             if (STATS) cnt.node_tests += 2;
         }
         if (cur == RT_CUR_DONE) break;
@@ -399,15 +461,16 @@ RT_DEV bool prim_first_hit(const PrimRec& R, float3 o, float3 d, float& t, float
 // prim_first_hit at the leaves, then the linear scan of the infinite primitives (records n_tris .. n_tris + n_planes) under
 // the running bound with strict `<` (:215-224).  hit.tri indexes `prims`; (hit.u, hit.v) = barycentrics or (t, aux).
 // skip_prim: see trace_nearest -- set by the caller only when a re-hit is impossible in exact arithmetic.
-template <class Space, bool STATS>
+template <class Space, bool STATS, int NODES = 0>
 RT_DEV void trace_nearest_gen(const Space& sp, const SceneLayout& L, SmemStack& st, float3 o, float3 d, int skip_prim, Hit& hit, Counters& cnt) {
-    const RaySetup r = ray_setup(o, d, L.nodes);
+    const RaySetup r = NODES == 2 ? ray_setup_quant(o, safe_inv_dir(d), L.qorg, L.qcell) : ray_setup(o, d, L.nodes);
     hit.t = RT_INF_F; hit.u = 0.f; hit.v = 0.f; hit.tri = -1;
     st.push(RT_CUR_DONE);
     int cur = 0;
     for (;;) {
         while (cur >= 0) {
-            pair_step(sp, L.nodes, r, hit.t, cur, st);
+            if constexpr (NODES == 2) pair_step_quant(sp, L.qnodes, r, hit.t, cur, st);
+            else pair_step(sp, L.nodes, r, hit.t, cur, st);
             if (STATS) cnt.node_tests += 2;
         }
         if (cur == RT_CUR_DONE) break;

@@ -328,6 +328,17 @@ static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bo
         case 6: return RT_DISPATCH(launch_wave_t, , MODE, 320, 2);        \
         default: return RT_DISPATCH(launch_wave_t, , MODE, 256, 2);       \
     }
+    if (a.L.quant && !a.L.general && !use_smem && variant == 3) {      // global-memory triangle scenes walk the quantised nodes (rt_api.cu flatten_scene)
+#define RT_QUANT(...) (stats ? launch_wave_t<GmemSpace, true, __VA_ARGS__, false, 2>(a, sms, s, info, launch, lanes) : launch_wave_t<GmemSpace, false, __VA_ARGS__, false, 2>(a, sms, s, info, launch, lanes))
+        switch (cfg) {
+            case 0: return RT_QUANT(1, 256, 2);
+            case 1: return RT_QUANT(1, 256, 3);
+            case 5: return RT_QUANT(1, 352, 2);
+            case 6: return RT_QUANT(1, 320, 2);
+            default: return RT_QUANT(1, 384, 2);
+        }
+#undef RT_QUANT
+    }
     if (a.L.general) {
         if (variant != 3) return cudaErrorInvalidValue;
         if (cfg == 0) return RT_DISPATCH(launch_wave_t, , 1, 256, 2, true);
@@ -342,10 +353,10 @@ static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bo
 cudaError_t launch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info) {
     return dispatch_render(a, variant, cfg, use_smem, stats, device_sms, stream, info, true, nullptr);
 }
-cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, bool general, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes) {
+cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, bool general, int node_format, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes) {
     RenderArgs a;
     memset(&a, 0, sizeof(a));
-    a.L.total_bytes = blob_bytes; a.stack_entries = stack_entries; a.L.general = general ? 1 : 0;
+    a.L.total_bytes = blob_bytes; a.stack_entries = stack_entries; a.L.general = general ? 1 : 0; a.L.quant = node_format == 2;
     return dispatch_render(a, variant, cfg, use_smem, stats, device_sms, 0, nullptr, false, lanes);
 }
 
@@ -454,6 +465,7 @@ __global__ void __launch_bounds__(128) trace_rays_kernel(const char* blob, const
     if (!F64) {
         Counters cnt; cnt.node_tests = 0; cnt.tri_tests = 0; cnt.light_tri_tests = 0;
         if (GEN) trace_nearest_gen<GmemSpace, false>(sp, L, st, o, d, -1, hit, cnt);
+        else if (L.quant) trace_nearest<GmemSpace, false, 2>(sp, L, st, o, d, -1, hit, cnt);      // the walk the render kernel of this scene runs
         else trace_nearest<GmemSpace, false>(sp, L, st, o, d, -1, hit, cnt);
         best = hit.tri; best_t = hit.tri >= 0 ? (double)hit.t : best_t;
     } else {

@@ -48,7 +48,7 @@ struct KernelInfo { int block, blocks_per_sm, regs, smem_bytes, grid; };
 // while-while / phased trace bursts; cfg picks the v3 build (block size x min blocks per SM).  use_smem: stage the blob in shared memory.  Returns cudaError_t.
 cudaError_t launch_render(const RenderArgs& a, int variant, int cfg, bool use_smem, bool stats, int device_sms, cudaStream_t stream, KernelInfo* info);
 // How many lanes the render kernel keeps resident (grid * block) -- used to size the sample chunks.
-cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, bool general, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
+cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, bool general, int node_format, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes);
 
 cudaError_t launch_black_layer(float4* layer, int W, int H, uint32_t tiles_x, uint32_t shard_index, uint32_t shard_count, float n_samples, cudaStream_t stream);
 cudaError_t launch_sum_layers(const float4* layers, int n_layers, size_t n_pix, float4* accum, bool add, cudaStream_t stream);

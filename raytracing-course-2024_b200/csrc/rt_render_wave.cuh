@@ -66,7 +66,9 @@ RT_DEV uint32_t pack_meta(int state, int depth, int attempt, uint32_t call) { re
 // BLOCK x MINB = resident threads per SM (occupancy / register budget trade-off, picked at run time from a few builds).
 // GEN: general-primitive scenes (SceneLayout::general): leaves hold 64-byte primitive records (triangles, boxes, ellipsoids),
 // the infinite primitives are scanned when a ray retires (rendering.rs:215-224), vertices may be dielectric (own spec).
-template <class Space, bool STATS, int MODE, int BLOCK, int MINB, bool GEN = false>
+// NODES: 0 = octant-ordered 112-byte pair nodes; 2 = quantised 32-byte pair nodes read with one 256-bit load (global-memory
+// triangle scenes: SceneLayout::qnodes, pair_step_quant).
+template <class Space, bool STATS, int MODE, int BLOCK, int MINB, bool GEN = false, int NODES = 0>
 __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderArgs a) {
     constexpr int P = RT_POOL_SLOTS;
     extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -112,16 +114,22 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
 
     // box-pair step and leaf step of the lane's ray (callers predicate them)
     auto node_step = [&]() {
-        pair_step<Space, true, IsSmem<Space>::value>(sp, L.nodes, rs, t_best, cur, st);   // shared-memory scenes always carry packed references
+        if constexpr (NODES == 2) pair_step_quant(sp, L.qnodes, rs, t_best, cur, st);
+        else pair_step<Space, true, IsSmem<Space>::value>(sp, L.nodes, rs, t_best, cur, st);   // shared-memory scenes always carry packed references
         if (STATS) cnt.node_tests += 2;
+    };
+    auto tri_rec = [&](int i) { return load_tri_test(sp, L.tri_t, i); };
+    // (origin, direction) of the lane's ray from the registers the box tests use: d = 1/(1/d), o = (o/d) d (3 MUFU + 3 FMUL, 2^-22
+    // relative) instead of six more shared-memory loads per leaf visit -- the kernel is shared-memory bound
+    auto ray_of_lane = [&](float3& o, float3& d) {
+        if constexpr (NODES == 2) ray_from_quant(rs, L.qorg, L.qcell, o, d);
+        else { d = f3(fast_rcp(rs.inv.x), fast_rcp(rs.inv.y), fast_rcp(rs.inv.z)); o = rs.od * d; }
     };
     auto leaf_step = [&]() {
         const uint32_t code = (uint32_t)~cur;
         const int first = (int)(code >> 3), n = (int)(code & 7u) + 1;
-        // direction and origin rebuilt from the registers the box tests use (d = 1/(1/d), o = (o/d) d: 3 MUFU + 3 FMUL,
-        // 2^-22 relative) instead of six more shared-memory loads per leaf visit -- the kernel is shared-memory bound
-        const float3 d = f3(fast_rcp(rs.inv.x), fast_rcp(rs.inv.y), fast_rcp(rs.inv.z));
-        const float3 o = rs.od * d;
+        float3 o, d;
+        ray_of_lane(o, d);
         const int skip_tri = pool.ldi(F_TRI, slot);
         if (GEN) {
             for (int i = first; i < first + n; ++i) {
@@ -136,8 +144,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
         if (small_leaves) {                                                // leaves of 1-2 triangles: both tests side by side, one update
             const int second = first + (n > 1 ? 1 : 0);
             float t0, u0, v0, t1, u1, v1;
-            const bool ok0 = tri_test(o, d, load_tri_test(sp, L.tri_t, first), t0, u0, v0) && first != skip_tri;
-            const bool ok1 = tri_test(o, d, load_tri_test(sp, L.tri_t, second), t1, u1, v1) && second != skip_tri && n > 1;
+            const bool ok0 = tri_test(o, d, tri_rec(first), t0, u0, v0) && first != skip_tri;
+            const bool ok1 = tri_test(o, d, tri_rec(second), t1, u1, v1) && second != skip_tri && n > 1;
             if (STATS) cnt.tri_tests += (unsigned long long)n;
             const bool take1 = ok1 && (!ok0 || t1 < t0);                   // strict <: the first triangle keeps exact ties (bvh.rs:269)
             const float tw = take1 ? t1 : t0;
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
         }
         for (int i = first; i < first + n; ++i) {
             float t, u, v;
-            const bool ok = tri_test(o, d, load_tri_test(sp, L.tri_t, i), t, u, v);
+            const bool ok = tri_test(o, d, tri_rec(i), t, u, v);
             if (STATS) cnt.tri_tests += 1;
             if (ok && t < t_best && i != skip_tri) { t_best = t; hit_tri = i; pool.stf(F_U, slot, u); pool.stf(F_V, slot, v); }
         }
@@ -162,8 +170,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
             if (fin != 0u) {
                 if (finished) {
                     if (GEN && L.n_planes > 0) {                                  // infinite primitives after the BVH (rendering.rs:215-224)
-                        const float3 d = f3(fast_rcp(rs.inv.x), fast_rcp(rs.inv.y), fast_rcp(rs.inv.z));
-                        const float3 o = rs.od * d;
+                        float3 o, d;
+                        ray_of_lane(o, d);
                         const int skip_tri = pool.ldi(F_TRI, slot);
                         for (int i = L.n_tris; i < L.n_tris + L.n_planes; ++i) {
                             float t, u, v;
@@ -184,7 +192,8 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 const int rank = __popc(idle & lt_mask);
                 if (slot < 0 && rank < tq_n) {
                     slot = pool.qld(0, (tq_head + rank) & (P - 1));
-                    rs.inv = pool.ld3(F_IX, slot); rs.od = pool.ld3(F_OX, slot) * rs.inv; ray_octant(rs, L.nodes);
+                    if constexpr (NODES == 2) rs = ray_setup_quant(pool.ld3(F_OX, slot), pool.ld3(F_IX, slot), L.qorg, L.qcell);
+                    else { rs.inv = pool.ld3(F_IX, slot); rs.od = pool.ld3(F_OX, slot) * rs.inv; ray_octant(rs, L.nodes); }
                     t_best = RT_INF_F; hit_tri = -1;
                     cur = 0; st.reset(stack0);
                     if (STATS) ++c_segments;
@@ -406,10 +415,10 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
     }
 }
 
-template <class Space, bool STATS, int MODE, int BLOCK, int MINB, bool GEN = false>
+template <class Space, bool STATS, int MODE, int BLOCK, int MINB, bool GEN = false, int NODES = 0>
 static cudaError_t launch_wave_t(const RenderArgs& a, int device_sms, cudaStream_t stream, KernelInfo* info, bool launch, int* lanes) {
     const uint32_t smem = a.stack_entries * BLOCK * 4u + (IsSmem<Space>::value ? a.L.total_bytes : 0u) + (BLOCK / 32) * RT_POOL_WARP_BYTES;
-    auto kern = render_wave_kernel<Space, STATS, MODE, BLOCK, MINB, GEN>;
+    auto kern = render_wave_kernel<Space, STATS, MODE, BLOCK, MINB, GEN, NODES>;
     cudaError_t e = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
     if (e != cudaSuccess) return e;
     int per_sm = 0;

@@ -606,6 +606,48 @@ def test_gpu_bvh_builder_gives_the_same_hits(gpu_rt, monkeypatch, name):
     host.close(); dev.close()
 
 
+@pytest.mark.parametrize("name", ["practice7_2", "practice7_3"])
+def test_quantised_nodes_walk_like_the_octant_nodes(gpu_rt, monkeypatch, name):
+    """Global-memory triangle scenes walk 32-byte nodes whose planes are 16-bit grid coordinates (rt_device.cuh pair_step_quant,
+    rt_api.cu quant_nodes; RT_NODE_FORMAT=0 keeps the 112-byte octant nodes).  The quantised boxes are conservative, so the
+    FP32 nearest hit must be the same triangle at the same distance -- for camera rays AND for rays that start up to 50 scene
+    diameters outside the mesh (the slack of the grid planes covers the FP32 rounding of far origins) -- and the rendered frame
+    must have the same path statistics."""
+    W = H = 192
+    monkeypatch.setenv("RT_NODE_FORMAT", "0")
+    octant = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 8)
+    monkeypatch.setenv("RT_NODE_FORMAT", "2")
+    quant = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 8)
+    monkeypatch.delenv("RT_NODE_FORMAT")
+    xs, ys = np.meshgrid(np.arange(W), np.arange(H))
+    xy = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.int32)
+    cam = octant.primary_rays(xy, np.full((xy.shape[0], 2), 0.5))
+    d = octant.desc()
+    v = np.asarray(d["tri_v"], np.float64).reshape(-1, 3)
+    lo, hi = v.min(axis=0), v.max(axis=0)
+    rng = np.random.default_rng(11)
+    n_far = 20000
+    target = lo + rng.random((n_far, 3)) * (hi - lo)
+    dirs = rng.normal(size=(n_far, 3)); dirs /= np.linalg.norm(dirs, axis=1, keepdims=True)
+    dist = np.linalg.norm(hi - lo) * rng.uniform(0.0, 50.0, size=(n_far, 1))
+    far = np.concatenate([target - dirs * dist, dirs], axis=1)
+    for rays, label in ((cam, "camera"), (far, "far origins")):
+        ia, ta = octant.trace_primary(rays, precision=32)
+        ib, tb = quant.trace_primary(rays, precision=32)
+        assert ((ia >= 0) == (ib >= 0)).all(), label
+        hit = ia >= 0
+        assert hit.mean() > 0.3, (label, hit.mean())
+        assert np.allclose(ta[hit], tb[hit], rtol=1e-6, atol=0.0), label            # same triangle arithmetic: a different id is a tie in t
+        assert (ia == ib).mean() > 0.995, (label, (ia == ib).mean())                   # (visiting order differs where entry distances tie: shared edges)
+    a, sa = octant.render_linear(seed=3, collect_stats=True)
+    b, sb = quant.render_linear(seed=3, collect_stats=True)
+    for k in ("samples", "segments", "vertices", "attempts"):
+        assert abs(sa[k] - sb[k]) <= 2e-4 * sa[k], (k, sa[k], sb[k])
+    assert sb["node_tests"] <= 1.02 * sa["node_tests"]                                # the grid costs < 2 % more box tests
+    assert abs(_lum(a.astype(np.float64)).mean() - _lum(b.astype(np.float64)).mean()) < 0.01 * _lum(a.astype(np.float64)).mean()
+    octant.close(); quant.close()
+
+
 def test_full_size_frame_properties(gpu_rt):
     """BASELINE.json's headline frame size (3840x2160, practice7_4) at a low sample count, through size-independent
     properties: every pixel receives exactly `spp` samples; the same seed gives identical bytes; two sample shards
