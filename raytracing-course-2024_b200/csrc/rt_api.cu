@@ -453,8 +453,9 @@ int flatten_scene(RtScene* s) {
     const int node_format = env_int("RT_NODE_FORMAT", 2);       // 0: octant-ordered pair nodes only, 2: + quantised 32-byte pair nodes (A/B knob)
     if (too_big_for_smem && !gen && node_format == 2 && (uint64_t)s->bvh.n_nodes * 32u <= 0x7fffffffull) {
         const std::vector<uint32_t> qn = quant_nodes(s->bvh, L.qorg, L.qcell);
-        L.qnodes = w.add(qn.data(), qn.size() * 4, 32);
-        L.quant = 1;
+        bool grid_ok = true;                                   // (a scene with non-finite or astronomically large coordinates keeps the octant nodes)
+        for (int a = 0; a < 3; ++a) grid_ok = grid_ok && std::isfinite(L.qorg[a]) && std::isfinite(L.qcell[a]) && L.qcell[a] < 1e30f;
+        if (grid_ok) { L.qnodes = w.add(qn.data(), qn.size() * 4, 32); L.quant = 1; }
     }
     if (s->blob_host.size() > 0xffffffffull || (uint64_t)std::max(s->bvh.n_nodes, s->light_bvh.n_nodes) * 128u > 0x7fffffffull)
         return fail(RT_ERR_LIMIT, "scene exceeds the 4 GiB device blob / 2 GiB node array addressed by 32-bit offsets");
