@@ -465,6 +465,7 @@ int flatten_scene(RtScene* s) {
     L.max_leaf = s->bvh.max_leaf;
     L.inv_n_lights = n_lights > 0 ? 1.0f / (float)n_lights : 0.0f;
     L.general = gen ? 1 : 0; L.n_planes = n_planes; L.has_dielectric = has_dielectric ? 1 : 0;
+    L.flat_scan = gen && n + n_planes <= env_int("RT_FLAT_SCAN_MAX", RT_FLAT_SCAN_MAX) ? 1 : 0;
 
     const int smem_limit = env_int("RT_SMEM_SCENE_MAX_BYTES", 48 * 1024);
     L.packed_refs = refs_packable(s->bvh) ? 1 : 0;
@@ -644,20 +645,20 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
     // through L1 / L2 -- two warps fewer per SM bring the blocks under 97 KB of shared memory each, which lets the driver pick the
     // 196 KB carve-out instead of 228 KB: 60 KB of L1 instead of 28 KB (measured: practice7_2 +4 %, practice7_3 +7 %)
     const int cfg_env = env_int("RT_WAVE_CFG", -1);
-    const int cfg_smem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : 2), cfg_gmem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : (s->L.quant ? 2 : 5));   // quantised walk: 384 x 2 again (the L1 is no longer the limit: +4 % over 352 x 2)
+    const int cfg_smem = cfg_env >= 0 ? cfg_env : (s->L.general && !s->L.flat_scan ? 6 : 2), cfg_gmem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : (s->L.quant ? 2 : 5));   // quantised walk: 384 x 2 again (the L1 is no longer the limit: +4 % over 352 x 2)
     // sample chunks: enough (pixel, chunk) items to keep every resident path slot busy many times over
     int lanes = 0;
     if (plan->use_smem && placement == 0) {
         // automatic placement: staging the scene must not cost occupancy (a mid-size blob can push the block past half of the
         // SM's shared memory: one block per SM instead of two) -- fall back to the global-memory path in that case
         int with_smem = 0, without = 0;
-        cudaError_t es = rtd::render_resident_lanes(plan->variant, cfg_smem, true, plan->stats, s->L.general != 0, s->L.quant ? 2 : 0, s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
+        cudaError_t es = rtd::render_resident_lanes(plan->variant, cfg_smem, true, plan->stats, s->L.general != 0, s->L.quant ? 2 : (s->L.flat_scan ? 3 : 0), s->L.total_bytes, s->stack_entries, s->sms, &with_smem);
         if (es != cudaSuccess) { cudaGetLastError(); with_smem = 0; }
-        CUDA_TRY(rtd::render_resident_lanes(plan->variant, cfg_gmem, false, plan->stats, s->L.general != 0, s->L.quant ? 2 : 0, s->L.total_bytes, s->stack_entries, s->sms, &without));
+        CUDA_TRY(rtd::render_resident_lanes(plan->variant, cfg_gmem, false, plan->stats, s->L.general != 0, s->L.quant ? 2 : (s->L.flat_scan ? 3 : 0), s->L.total_bytes, s->stack_entries, s->sms, &without));
         if (with_smem < without * 9 / 10) { plan->use_smem = false; a.blob = s->blob_dev; }     // (352 x 2 keeps 8 % fewer lanes than 384 x 2: not a reason to leave shared memory)
     }
     plan->cfg = plan->use_smem ? cfg_smem : cfg_gmem;
-    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.general != 0, s->L.quant ? 2 : 0, s->L.total_bytes, s->stack_entries, s->sms, &lanes));
+    CUDA_TRY(rtd::render_resident_lanes(plan->variant, plan->cfg, plan->use_smem, plan->stats, s->L.general != 0, s->L.quant ? 2 : (s->L.flat_scan ? 3 : 0), s->L.total_bytes, s->stack_entries, s->sms, &lanes));
     const int n_samp = s1 - s0;
     // measured (B200): work items ~32x the resident path slots keep the end-of-frame tail short (512x512x1024 spp: +16 % over
     // 4x); frames with plenty of pixels still get up to 4 chunks of >= 128 samples (3840x2160x1024: +0.7 %)

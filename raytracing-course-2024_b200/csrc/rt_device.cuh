@@ -94,8 +94,10 @@ struct SceneLayout {
     uint32_t qnodes;                             // 32-byte aligned
     int32_t quant;
     float qorg[3], qcell[3];                     // plane = qorg + q * qcell
+    int32_t flat_scan;                           // general scene of <= RT_FLAT_SCAN_MAX primitives: the render kernel scans `prims` instead of walking `nodes`
 };
 #define RT_BRUTE_LIGHTS 8
+#define RT_FLAT_SCAN_MAX 12
 
 struct SmemSpace {
     uint32_t base;  // shared-window address of the blob

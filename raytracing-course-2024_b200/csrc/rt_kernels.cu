@@ -339,6 +339,16 @@ static cudaError_t dispatch_render(const RenderArgs& a, int variant, int cfg, bo
         }
 #undef RT_QUANT
     }
+    if (a.L.general && a.L.flat_scan && use_smem && variant == 3) {    // a handful of primitives: no tree, one scan per trace burst
+#define RT_FLAT(...) (stats ? launch_wave_t<SmemSpace, true, __VA_ARGS__, true, 3>(a, sms, s, info, launch, lanes) : launch_wave_t<SmemSpace, false, __VA_ARGS__, true, 3>(a, sms, s, info, launch, lanes))
+        switch (cfg) {
+            case 0: return RT_FLAT(1, 256, 2);
+            case 1: return RT_FLAT(1, 256, 3);
+            case 2: return RT_FLAT(1, 384, 2);
+            default: return RT_FLAT(1, 320, 2);
+        }
+#undef RT_FLAT
+    }
     if (a.L.general) {
         if (variant != 3) return cudaErrorInvalidValue;
         if (cfg == 0) return RT_DISPATCH(launch_wave_t, , 1, 256, 2, true);
@@ -356,7 +366,7 @@ cudaError_t launch_render(const RenderArgs& a, int variant, int cfg, bool use_sm
 cudaError_t render_resident_lanes(int variant, int cfg, bool use_smem, bool stats, bool general, int node_format, uint32_t blob_bytes, uint32_t stack_entries, int device_sms, int* lanes) {
     RenderArgs a;
     memset(&a, 0, sizeof(a));
-    a.L.total_bytes = blob_bytes; a.stack_entries = stack_entries; a.L.general = general ? 1 : 0; a.L.quant = node_format == 2;
+    a.L.total_bytes = blob_bytes; a.stack_entries = stack_entries; a.L.general = general ? 1 : 0; a.L.quant = node_format == 2; a.L.flat_scan = node_format == 3;
     return dispatch_render(a, variant, cfg, use_smem, stats, device_sms, 0, nullptr, false, lanes);
 }
 

@@ -67,7 +67,9 @@ RT_DEV uint32_t pack_meta(int state, int depth, int attempt, uint32_t call) { re
 // GEN: general-primitive scenes (SceneLayout::general): leaves hold 64-byte primitive records (triangles, boxes, ellipsoids),
 // the infinite primitives are scanned when a ray retires (rendering.rs:215-224), vertices may be dielectric (own spec).
 // NODES: 0 = octant-ordered 112-byte pair nodes; 2 = quantised 32-byte pair nodes read with one 256-bit load (global-memory
-// triangle scenes: SceneLayout::qnodes, pair_step_quant).
+// triangle scenes: SceneLayout::qnodes, pair_step_quant); 3 = NO tree (general scenes of a handful of primitives, SceneLayout::flat_scan):
+// a trace burst is one straight scan over all records -- every lane reads the same record (broadcast loads), the primitive kind is
+// warp-uniform, all 32 rays finish together: no box tests, no phase votes, no plane scan at retire.
 template <class Space, bool STATS, int MODE, int BLOCK, int MINB, bool GEN = false, int NODES = 0>
 __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderArgs a) {
     constexpr int P = RT_POOL_SLOTS;
@@ -169,7 +171,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
             const unsigned fin = __ballot_sync(FULL, finished);
             if (fin != 0u) {
                 if (finished) {
-                    if (GEN && L.n_planes > 0) {                                  // infinite primitives after the BVH (rendering.rs:215-224)
+                    if (GEN && NODES != 3 && L.n_planes > 0) {                    // infinite primitives after the BVH (rendering.rs:215-224)
                         float3 o, d;
                         ray_of_lane(o, d);
                         const int skip_tri = pool.ldi(F_TRI, slot);
@@ -193,7 +195,7 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
                 if (slot < 0 && rank < tq_n) {
                     slot = pool.qld(0, (tq_head + rank) & (P - 1));
                     if constexpr (NODES == 2) rs = ray_setup_quant(pool.ld3(F_OX, slot), pool.ld3(F_IX, slot), L.qorg, L.qcell);
-                    else { rs.inv = pool.ld3(F_IX, slot); rs.od = pool.ld3(F_OX, slot) * rs.inv; ray_octant(rs, L.nodes); }
+                    else if constexpr (NODES != 3) { rs.inv = pool.ld3(F_IX, slot); rs.od = pool.ld3(F_OX, slot) * rs.inv; ray_octant(rs, L.nodes); }
                     t_best = RT_INF_F; hit_tri = -1;
                     cur = 0; st.reset(stack0);
                     if (STATS) ++c_segments;
@@ -370,6 +372,24 @@ __global__ void __launch_bounds__(BLOCK, MINB) render_wave_kernel(const RenderAr
         if (__ballot_sync(FULL, slot >= 0) == 0u) break;                         // nothing in flight, nothing queued: pool exhausted
 
         // ---------------------------------------------------------------------------------- trace burst
+        if constexpr (NODES == 3) {
+            // intersect_ray_with_scene (rendering.rs:201-226) as one scan: finite primitives in BVH order, then the planes, strict `<`
+            if (slot >= 0) {
+                const float3 o = pool.ld3(F_OX, slot), iv = pool.ld3(F_IX, slot);
+                const float3 d = f3(fast_rcp(iv.x), fast_rcp(iv.y), fast_rcp(iv.z));
+                const int skip_tri = pool.ldi(F_TRI, slot);
+                float hu = 0.f, hv = 0.f;
+                for (int i = 0; i < L.n_tris + L.n_planes; ++i) {
+                    float t, u, v;
+                    const bool ok = prim_first_hit(load_prim(sp, L.prims, i), o, d, t, u, v);
+                    if (ok && t < t_best && i != skip_tri) { t_best = t; hit_tri = i; hu = u; hv = v; }
+                }
+                if (STATS) cnt.tri_tests += (unsigned long long)(L.n_tris + L.n_planes);
+                pool.stf(F_U, slot, hu); pool.stf(F_V, slot, hv);
+                cur = RT_CUR_DONE;
+            }
+            continue;
+        }
         if (MODE == 0) {
             for (;;) {
                 while (cur >= 0) node_step();

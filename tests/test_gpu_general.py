@@ -259,6 +259,32 @@ def test_native_size_text_scenes(gpu_rt, name, W, H, ospp):
     sc.close()
 
 
+@pytest.mark.parametrize("name", ["practice3_1", "practice3_4", "practice3_5"])
+def test_flat_scan_renders_what_the_tree_walk_renders(gpu_rt, monkeypatch, name):
+    """Text scenes of <= RT_FLAT_SCAN_MAX (12) primitives are intersected without a tree: one scan over all records per trace
+    burst (rt_render_wave.cuh NODES = 3; RT_FLAT_SCAN_MAX=0 restores the BVH walk + plane scan of rendering.rs:201-226).  Same
+    Philox counters, same primitive tests, same strict `<` in the same order (finite primitives in BVH order, then the planes):
+    the two kernels must produce the same path statistics and -- up to FP32 rounding of the ray the tree walk rebuilds from
+    (1/d, o/d), and exact ties -- the same image."""
+    W = H = 96
+    monkeypatch.setenv("RT_FLAT_SCAN_MAX", "0")
+    tree = gpu_rt.Scene.from_text(text_path(name), W, H, 32)
+    monkeypatch.delenv("RT_FLAT_SCAN_MAX")
+    flat = gpu_rt.Scene.from_text(text_path(name), W, H, 32)
+    a, sa = tree.render_linear(seed=5, collect_stats=True)
+    b, sb = flat.render_linear(seed=5, collect_stats=True)
+    assert sa["node_tests"] > 0 and sb["node_tests"] == 0                               # the flat kernel really ran
+    info = flat.info()
+    assert sb["tri_tests"] == sb["segments"] * (info["n_tris"] + info["n_infinite"])    # every record, every segment
+    for k in ("samples", "segments", "vertices", "attempts"):
+        assert abs(sa[k] - sb[k]) <= 2e-4 * sa[k], (k, sa[k], sb[k])
+    la, lb = _lum(a.astype(np.float64)), _lum(b.astype(np.float64))
+    assert abs(la.mean() - lb.mean()) <= 2e-3 * la.mean(), (la.mean(), lb.mean())
+    close = np.abs(la - lb) <= 0.02 * la.mean() + 1e-3 * la
+    assert close.mean() >= 0.99, close.mean()
+    tree.close(); flat.close()
+
+
 def test_cli_renders_text_scenes(gpu_rt, tmp_path):
     """`raytracing-engine scene.txt out.ppm` (the text era's argv) and the 5-argument form of main.rs:37-43 with a .txt scene:
     the file's DIMENSIONS / SAMPLES unless the arguments override them; bytes == rt_render."""
