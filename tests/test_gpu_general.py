@@ -285,6 +285,28 @@ def test_flat_scan_renders_what_the_tree_walk_renders(gpu_rt, monkeypatch, name)
     tree.close(); flat.close()
 
 
+def test_scene_of_infinite_primitives_only(gpu_rt, monkeypatch, tmp_path):
+    """scene.rs:37 `infinite_primitives` with an EMPTY `bvh_finite_primitives`: two planes under a sky, no finite primitive, no light.
+    The flat scan and the tree walk (whose filler leaf points at record 0) must agree exactly."""
+    path = tmp_path / "planes.txt"
+    path.write_text("DIMENSIONS 48 32\nRAY_DEPTH 4\nSAMPLES 32\nBG_COLOR 0.6 0.7 0.9\nCAMERA_POSITION 0 1 5\nCAMERA_RIGHT 1 0 0\nCAMERA_UP 0 1 0\n"
+                    "CAMERA_FORWARD 0 0 -1\nCAMERA_FOV_X 1.0\n\nNEW_PRIMITIVE\nPLANE 0 1 0\nPOSITION 0 0 0\nCOLOR 0.8 0.3 0.3\n\n"
+                    "NEW_PRIMITIVE\nPLANE 0 0 1\nPOSITION 0 0 -4\nCOLOR 0.3 0.8 0.3\n")
+    res = {}
+    for cap in ("0", "12"):
+        monkeypatch.setenv("RT_FLAT_SCAN_MAX", cap)
+        sc = gpu_rt.Scene.from_file(str(path), 0, 0, 0)
+        info = sc.info()
+        assert info["n_tris"] == 0 and info["n_infinite"] == 2
+        img, st = sc.render_linear(seed=2, collect_stats=True)
+        res[cap] = (img.astype(np.float64), st)
+        sc.close()
+    assert res["0"][1]["node_tests"] > 0 and res["12"][1]["node_tests"] == 0
+    assert res["0"][1]["segments"] == res["12"][1]["segments"] and res["12"][1]["tri_tests"] == 2 * res["12"][1]["segments"]
+    assert np.isfinite(res["12"][0]).all() and res["12"][0].mean() > 0.1
+    assert np.allclose(res["0"][0], res["12"][0], rtol=1e-4, atol=1e-6)
+
+
 def test_cli_renders_text_scenes(gpu_rt, tmp_path):
     """`raytracing-engine scene.txt out.ppm` (the text era's argv) and the 5-argument form of main.rs:37-43 with a .txt scene:
     the file's DIMENSIONS / SAMPLES unless the arguments override them; bytes == rt_render."""
