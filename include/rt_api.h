@@ -169,6 +169,11 @@ int rt_scene_set_frame(RtScene* scene, int32_t width, int32_t height, int32_t sa
  * child0 min xyz,max xyz, child1 min xyz,max xyz, child0 ref, child1 ref (refs as floats of the int encoding:
  * >= 0 inner node index, < 0 leaf ~((first << 3) | (count-1))); tri_order: n_tris original triangle ids. */
 int rt_scene_get_bvh(const RtScene* scene, float* nodes, int32_t* tri_order);
+/* The QUANTISED copy of the same tree that triangle scenes too large for shared memory walk on the device (32 bytes per pair node:
+ * words 0 / 1 = x minima / maxima of child 0 (low 16 bits) and child 1 (high 16 bits), 2 / 3 = y, 4 / 5 = z, 6 / 7 = the child references
+ * with inner nodes as byte offsets index * 32); plane = grid6[axis] + q * grid6[3 + axis].  *present = 0 (and nothing written) for scenes
+ * that keep the full-precision nodes only.  For the containment check of the quantisation (every grid box encloses its f32 box). */
+int rt_scene_get_quantised_bvh(const RtScene* scene, uint32_t* words, float* grid6, int32_t* present);
 
 /* ---- the hot path ---------------------------------------------------------------------------------------- */
 /* Replaces render_scene(&scene) -> Vec<u8>  (rendering.rs:21-69): W*H*3 bytes, RGB8, row-major, row 0 = top.

@@ -116,6 +116,7 @@ def lib():
         L.rt_scene_info.argtypes = [vp, C.POINTER(RtSceneInfo)]
         L.rt_scene_set_frame.argtypes = [vp, C.c_int32, C.c_int32, C.c_int32]
         L.rt_scene_get_bvh.argtypes = [vp, C.POINTER(C.c_float), C.POINTER(C.c_int32)]
+        L.rt_scene_get_quantised_bvh.argtypes = [vp, C.POINTER(C.c_uint32), C.POINTER(C.c_float), C.POINTER(C.c_int32)]
         L.rt_render.argtypes = [vp, C.POINTER(RtRenderParams), C.POINTER(C.c_uint8), C.POINTER(RtStats)]
         L.rt_render_linear.argtypes = [vp, C.POINTER(RtRenderParams), C.POINTER(C.c_float), C.POINTER(RtStats)]
         L.rt_render_accumulate_device.argtypes = [vp, C.POINTER(RtRenderParams), vp, vp, C.POINTER(RtStats)]
@@ -284,6 +285,13 @@ class Scene:
         order = np.zeros(max(i["n_tris"], 1), dtype=np.int32)
         _check(lib().rt_scene_get_bvh(self._h, nodes.ctypes.data_as(C.POINTER(C.c_float)), order.ctypes.data_as(C.POINTER(C.c_int32))))
         return nodes, order[: i["n_tris"]]
+
+    def quantised_bvh(self):
+        """(words (n_nodes, 8) uint32, grid origin (3,), grid cell (3,)) of the quantised node array, or None when the scene has none."""
+        n = self.info()["n_nodes"]
+        words, grid, present = np.zeros((n, 8), dtype=np.uint32), np.zeros(6, dtype=np.float32), C.c_int32(0)
+        _check(lib().rt_scene_get_quantised_bvh(self._h, words.ctypes.data_as(C.POINTER(C.c_uint32)), grid.ctypes.data_as(C.POINTER(C.c_float)), C.byref(present)))
+        return (words, grid[:3].copy(), grid[3:].copy()) if present.value else None
 
     # -- the hot path -------------------------------------------------------------------------------------------
     def render(self, **kw):

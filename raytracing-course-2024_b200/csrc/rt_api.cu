@@ -944,6 +944,15 @@ int rt_scene_get_bvh(const RtScene* s, float* nodes, int32_t* tri_order) {
     return RT_OK;
 }
 
+int rt_scene_get_quantised_bvh(const RtScene* s, uint32_t* words, float* grid6, int32_t* present) {
+    if (!s || !present) return fail(RT_ERR_INVALID, "null argument");
+    *present = s->L.quant ? 1 : 0;
+    if (!s->L.quant) return RT_OK;
+    if (words) std::memcpy(words, s->blob_host.data() + s->L.qnodes, (size_t)s->bvh.n_nodes * 32u);
+    if (grid6) for (int a = 0; a < 3; ++a) { grid6[a] = s->L.qorg[a]; grid6[3 + a] = s->L.qcell[a]; }
+    return RT_OK;
+}
+
 // render_scene (rendering.rs:21-69)
 int rt_render(RtScene* s, const RtRenderParams* p, uint8_t* rgb_out, RtStats* st) {
     if (!s || !rgb_out) return fail(RT_ERR_INVALID, "null argument");

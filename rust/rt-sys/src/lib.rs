@@ -155,6 +155,7 @@ extern "C" {
     pub fn rt_scene_info(scene: *const RtScene, out: *mut RtSceneInfo) -> c_int;
     pub fn rt_scene_set_frame(scene: *mut RtScene, width: i32, height: i32, samples: i32) -> c_int;
     pub fn rt_scene_get_bvh(scene: *const RtScene, nodes: *mut f32, tri_order: *mut i32) -> c_int;
+    pub fn rt_scene_get_quantised_bvh(scene: *const RtScene, words: *mut u32, grid6: *mut f32, present: *mut i32) -> c_int;
 
     pub fn rt_render(scene: *mut RtScene, params: *const RtRenderParams, rgb_out: *mut u8, stats: *mut RtStats) -> c_int;
     pub fn rt_render_linear(scene: *mut RtScene, params: *const RtRenderParams, rgb_linear_out: *mut f32, stats: *mut RtStats) -> c_int;

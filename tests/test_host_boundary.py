@@ -122,6 +122,38 @@ def test_flat_bvh_walk_matches_oracle_hits(rt, oracle, name):
     sc.close()
 
 
+@pytest.mark.parametrize("name", ["practice7_2", "practice7_3"])
+def test_quantised_nodes_enclose_the_full_precision_nodes(rt, name):
+    """Triangle scenes too large for shared memory walk 32-byte nodes whose planes are 16-bit coordinates on a global grid
+    (rt_api.cu quant_nodes, rt_device.cuh pair_step_quant).  Containment check in the spirit of validate_bvh (bvh.rs:299-322):
+    every grid box, reconstructed with the float constants the device uses, encloses the f32 box of the same child with at least
+    1.5 cells of slack (what absorbs the FP32 plane evaluation) and at most 5 (tightness); the references describe the same tree."""
+    sc = rt.Scene.from_gltf(scene_path(name), 8, 8, 1, device=-1)
+    nodes, _ = sc.bvh()
+    q = sc.quantised_bvh()
+    assert q is not None, "large meshes carry quantised nodes"
+    words, org, cell = q
+    assert words.shape == (nodes.shape[0], 8) and (cell > 0).all()
+    org, cell = org.astype(np.float64), cell.astype(np.float64)
+    for child in (0, 1):
+        lo = nodes[:, child * 6:child * 6 + 3].astype(np.float64)
+        hi = nodes[:, child * 6 + 3:child * 6 + 6].astype(np.float64)
+        shift = 16 * child
+        qlo = np.stack([(words[:, 2 * a] >> shift) & 0xffff for a in range(3)], axis=1).astype(np.float64)
+        qhi = np.stack([(words[:, 2 * a + 1] >> shift) & 0xffff for a in range(3)], axis=1).astype(np.float64)
+        plo, phi = org + qlo * cell, org + qhi * cell
+        assert (plo <= lo - 1.5 * cell + 1e-9 * np.abs(lo)).all() and (phi >= hi + 1.5 * cell - 1e-9 * np.abs(hi)).all()
+        assert (plo >= lo - 5.0 * cell).all() and (phi <= hi + 5.0 * cell).all()
+        ref_f = nodes[:, 12 + child].astype(np.int64)
+        ref_q = words[:, 6 + child].astype(np.uint32).view(np.int32).astype(np.int64)
+        inner = ref_f >= 0
+        assert ((ref_q >= 0) == inner).all()
+        assert (ref_q[inner] == ref_f[inner] * 32).all() and (ref_q[~inner] == ref_f[~inner]).all()
+    small = rt.Scene.from_gltf(scene_path("practice7_4"), 8, 8, 1, device=-1)
+    assert small.quantised_bvh() is None                     # shared-memory scenes keep the packed full-precision nodes only
+    sc.close(); small.close()
+
+
 def test_host_only_scene_refuses_compute_and_reports_errors(rt, tmp_path):
     sc = rt.Scene.from_gltf(scene_path("practice7_1"), 8, 8, 1, device=-1)
     with pytest.raises(rt.RtError) as e:

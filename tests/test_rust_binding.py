@@ -13,7 +13,7 @@ from conftest import ROOT
 HEADER = os.path.join(ROOT, "include", "rt_api.h")
 LIB_RS = os.path.join(ROOT, "rust", "rt-sys", "src", "lib.rs")
 
-C_TO_RUST = {"int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "uint8_t": "u8", "double": "f64", "float": "f32", "int": "c_int", "char": "c_char",
+C_TO_RUST = {"int32_t": "i32", "int64_t": "i64", "uint64_t": "u64", "uint32_t": "u32", "uint8_t": "u8", "double": "f64", "float": "f32", "int": "c_int", "char": "c_char",
              "void": "c_void"}
 CTYPES = {"i32": C.c_int32, "i64": C.c_int64, "u64": C.c_uint64, "f64": C.c_double, "f32": C.c_float}
 
