@@ -307,6 +307,20 @@ def test_scene_of_infinite_primitives_only(gpu_rt, monkeypatch, tmp_path):
     assert np.allclose(res["0"][0], res["12"][0], rtol=1e-4, atol=1e-6)
 
 
+def test_u8_bytes_of_negative_radiance_follow_the_reference_tonemap(gpu_rt, oracle):
+    """The reference's estimator produces negative pixel sums (weight on the geometric normal, acceptance on the shading normal --
+    object space for the rotated box of practice3_5).  color_to_pixel (rendering.rs:236-262) feeds them through the ACES rational
+    and saturates AFTERWARDS, so a negative radiance is not simply black: the bytes must be the oracle's for every pixel."""
+    sc = gpu_rt.Scene.from_text(text_path("practice3_5"), 160, 160, 4)
+    u8, _ = sc.render(seed=9)
+    lin, _ = sc.render_linear(seed=9)
+    lin = lin.astype(np.float64)
+    assert (lin < 0).any(axis=2).sum() >= 5, "this frame is expected to contain negative pixels"
+    exp = oracle.color_to_pixel(lin.reshape(-1, 3)).reshape(u8.shape)
+    assert np.array_equal(u8, exp)
+    sc.close()
+
+
 def test_cli_renders_text_scenes(gpu_rt, tmp_path):
     """`raytracing-engine scene.txt out.ppm` (the text era's argv) and the 5-argument form of main.rs:37-43 with a .txt scene:
     the file's DIMENSIONS / SAMPLES unless the arguments override them; bytes == rt_render."""
