@@ -41,6 +41,7 @@ struct Build {
     std::vector<int32_t> order;    // being permuted
     std::vector<TempNode> nodes;
     std::vector<double> right_area;
+    std::vector<double> weight;    // per original id: what one more box of this primitive costs (1 for a triangle, the triangle count of a subtree); empty = all 1
 
     int build(int first, int count, int depth, int* max_depth) {
         TempNode n;
@@ -59,9 +60,12 @@ struct Build {
             Box acc; acc.reset();
             for (int i = count - 1; i > 0; --i) { acc.grow(boxes[(size_t)order[(size_t)(first + i)]]); right_area[(size_t)i] = acc.half_area(); }
             acc.reset();
+            double total_w = (double)count, left_w = 0.0;
+            if (!weight.empty()) { total_w = 0.0; for (int i = 0; i < count; ++i) total_w += weight[(size_t)order[(size_t)(first + i)]]; }
             for (int i = 0; i + 1 < count; ++i) {
                 acc.grow(boxes[(size_t)order[(size_t)(first + i)]]);
-                double cost = (double)(i + 1) * acc.half_area() + (double)(count - i - 1) * right_area[(size_t)(i + 1)];
+                left_w += weight.empty() ? 1.0 : weight[(size_t)order[(size_t)(first + i)]];
+                double cost = left_w * acc.half_area() + (total_w - left_w) * right_area[(size_t)(i + 1)];
                 if (cost < best_cost) { best_cost = cost; best_axis = axis; best_split = i + 1; }
             }
         }
@@ -132,9 +136,10 @@ void quat_to_matrix(const double* q, double* m) {
     m[6] = 2 * (i * k - j * w);     m[7] = 2 * (j * k + i * w);     m[8] = 1 - 2 * (i * i + j * j);
 }
 
-void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out) {
+void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out, const std::vector<double>* weights) {
     *out = FlatBvh();
-    Build b{p, {}, ids, {}, {}};
+    Build b{p, {}, ids, {}, {}, {}};
+    if (weights) b.weight = *weights;
     int32_t max_id = -1;
     for (int32_t id : ids) max_id = std::max(max_id, id);
     b.boxes.resize((size_t)(max_id + 1));
@@ -161,6 +166,107 @@ void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, 
         out->child[0] = leaf_ref(0, (int)ids.size()); out->child[1] = leaf_ref(0, 1);
         out->n_leaves = 1; out->max_leaf = (int)ids.size(); out->depth = 2;
     }
+}
+
+// GPU LBVH -> better top of the tree.  The Morton-code hierarchy is good locally and poor globally (it splits space, not surface
+// area), and the top levels are the ones every ray walks.  Cut the tree into ~n_clusters subtrees (largest surface area first),
+// rebuild the part above the cut with the host's full-sweep SAH over the subtree boxes (weighted by their triangle counts) and
+// graft the untouched subtrees below it.  Milliseconds for a few thousand clusters; leaves and tri_order do not change.
+void regraft_top_sah(FlatBvh* bvh, int n_clusters, const BvhBuildParams& p) {
+    const int N = bvh->n_nodes;
+    n_clusters = std::min(n_clusters, N / 3);                 // the cut needs room below it
+    if (n_clusters < 8) return;
+    auto slot_box = [bvh](int node, int s) {
+        const float* A = &bvh->box_a[(size_t)node * 4]; const float* B = &bvh->box_b[(size_t)node * 4]; const float* C = &bvh->box_c[(size_t)node * 4];
+        const float* xy = s == 0 ? A : B;
+        BoxD b;
+        b.mn[0] = xy[0]; b.mx[0] = xy[1]; b.mn[1] = xy[2]; b.mx[1] = xy[3]; b.mn[2] = C[s * 2]; b.mx[2] = C[s * 2 + 1];
+        return b;
+    };
+    // triangles below every node (iterative post-order; the GPU builder's node order is not specified)
+    std::vector<int32_t> tris((size_t)N, -1);
+    {
+        std::vector<int32_t> st(1, 0);
+        while (!st.empty()) {
+            const int32_t n = st.back();
+            int32_t sum = 0; bool ready = true;
+            for (int c = 0; c < 2; ++c) {
+                const int32_t r = bvh->child[(size_t)n * 2 + (size_t)c];
+                if (r < 0) sum += (int32_t)((uint32_t)(~r) & 7u) + 1;
+                else if (tris[(size_t)r] < 0) { st.push_back(r); ready = false; }
+                else sum += tris[(size_t)r];
+            }
+            if (ready) { tris[(size_t)n] = sum; st.pop_back(); }
+        }
+    }
+    struct Elem { BoxD box; int32_t ref; double area; };
+    auto elem = [&](int node, int s) {
+        Elem e; e.box = slot_box(node, s); e.ref = bvh->child[(size_t)node * 2 + (size_t)s];
+        const double x = e.box.mx[0] - e.box.mn[0], y = e.box.mx[1] - e.box.mn[1], z = e.box.mx[2] - e.box.mn[2];
+        e.area = x * y + y * z + z * x;
+        return e;
+    };
+    std::vector<Elem> done;                                   // leaves met on the way: part of the frontier as they are
+    auto cmp = [](const Elem& a, const Elem& b) { return a.area < b.area; };
+    std::vector<Elem> heap;
+    std::vector<char> dropped((size_t)N, 0);
+    dropped[0] = 1;
+    for (int s = 0; s < 2; ++s) { Elem e = elem(0, s); if (e.ref >= 0) { heap.push_back(e); std::push_heap(heap.begin(), heap.end(), cmp); } else done.push_back(e); }
+    while (!heap.empty() && (int)(heap.size() + done.size()) < n_clusters) {
+        std::pop_heap(heap.begin(), heap.end(), cmp);
+        const Elem top = heap.back(); heap.pop_back();
+        dropped[(size_t)top.ref] = 1;
+        for (int s = 0; s < 2; ++s) { Elem e = elem(top.ref, s); if (e.ref >= 0) { heap.push_back(e); std::push_heap(heap.begin(), heap.end(), cmp); } else done.push_back(e); }
+    }
+    std::vector<Elem> frontier = done;
+    frontier.insert(frontier.end(), heap.begin(), heap.end());
+    const int K = (int)frontier.size();
+    if (K < 8) return;
+    std::vector<BoxD> boxes((size_t)K); std::vector<int32_t> ids((size_t)K); std::vector<double> w((size_t)K);
+    for (int k = 0; k < K; ++k) {
+        boxes[(size_t)k] = frontier[(size_t)k].box; ids[(size_t)k] = k;
+        const int32_t r = frontier[(size_t)k].ref;
+        w[(size_t)k] = r >= 0 ? (double)tris[(size_t)r] : (double)(((uint32_t)(~r) & 7u) + 1);
+    }
+    BvhBuildParams tp = p; tp.max_leaf_size = 1;              // a leaf of the top tree is exactly one subtree
+    FlatBvh T;
+    build_bvh(boxes, ids, tp, &T, &w);
+    // new numbering: the top tree first, then the surviving nodes in their old order
+    std::vector<int32_t> map((size_t)N, -1);
+    int32_t next = T.n_nodes;
+    for (int n = 0; n < N; ++n) if (!dropped[(size_t)n]) map[(size_t)n] = next++;
+    FlatBvh out;
+    out.n_nodes = next; out.n_leaves = bvh->n_leaves; out.max_leaf = bvh->max_leaf; out.tri_order = bvh->tri_order;
+    out.box_a.resize((size_t)next * 4); out.box_b.resize((size_t)next * 4); out.box_c.resize((size_t)next * 4); out.child.resize((size_t)next * 2);
+    for (int n = 0; n < T.n_nodes; ++n) {
+        for (int k = 0; k < 4; ++k) { out.box_a[(size_t)n * 4 + k] = T.box_a[(size_t)n * 4 + k]; out.box_b[(size_t)n * 4 + k] = T.box_b[(size_t)n * 4 + k]; out.box_c[(size_t)n * 4 + k] = T.box_c[(size_t)n * 4 + k]; }
+        for (int c = 0; c < 2; ++c) {
+            int32_t r = T.child[(size_t)n * 2 + (size_t)c];
+            if (r < 0) {                                                        // top leaf = frontier element
+                const int32_t fr = frontier[(size_t)T.tri_order[(size_t)((uint32_t)(~r) >> 3)]].ref;
+                r = fr >= 0 ? map[(size_t)fr] : fr;
+            }
+            out.child[(size_t)n * 2 + (size_t)c] = r;
+        }
+    }
+    for (int n = 0; n < N; ++n) {
+        if (dropped[(size_t)n]) continue;
+        const size_t m = (size_t)map[(size_t)n];
+        for (int k = 0; k < 4; ++k) { out.box_a[m * 4 + k] = bvh->box_a[(size_t)n * 4 + k]; out.box_b[m * 4 + k] = bvh->box_b[(size_t)n * 4 + k]; out.box_c[m * 4 + k] = bvh->box_c[(size_t)n * 4 + k]; }
+        for (int c = 0; c < 2; ++c) { const int32_t r = bvh->child[(size_t)n * 2 + (size_t)c]; out.child[m * 2 + (size_t)c] = r >= 0 ? map[(size_t)r] : r; }
+    }
+    // depth of the grafted tree (a leaf below a node at depth d sits at d + 1, like the host builder counts)
+    int depth = 0;
+    std::vector<std::pair<int32_t, int>> st(1, std::make_pair(0, 1));
+    while (!st.empty()) {
+        const std::pair<int32_t, int> it = st.back(); st.pop_back();
+        for (int c = 0; c < 2; ++c) {
+            const int32_t r = out.child[(size_t)it.first * 2 + (size_t)c];
+            if (r >= 0) st.push_back(std::make_pair(r, it.second + 1)); else depth = std::max(depth, it.second + 1);
+        }
+    }
+    out.depth = depth;
+    *bvh = out;
 }
 
 int validate_flat_bvh(const FlatBvh& bvh, const std::vector<BoxD>& boxes) {

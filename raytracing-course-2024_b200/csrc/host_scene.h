@@ -65,7 +65,11 @@ struct BvhBuildParams {
 };
 
 // boxes: per primitive id (load order), EPS-padded like aabb.rs:53-94; ids: which primitives to include (the finite ones, or the lights).
-void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out);
+// weights (optional, per primitive id): SAH weight of a primitive (default 1; regraft_top_sah passes the triangle count of a subtree).
+void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, const BvhBuildParams& p, FlatBvh* out, const std::vector<double>* weights = nullptr);
+// Rebuilds the TOP of a tree (above a cut of ~n_clusters subtrees, largest surface area first) with the SAH sweep and grafts the
+// subtrees back: the repair of the GPU LBVH's globally poor splits.  n_clusters is capped at a third of the node count; < 8: no-op.
+void regraft_top_sah(FlatBvh* bvh, int n_clusters, const BvhBuildParams& p);
 // GPU builder (rt_bvh_gpu.cu): Morton codes + radix sort + Karras hierarchy + refit + collapse to leaves <= max_leaf_size.
 // Same output format; lower tree quality than the SAH sweep, milliseconds instead of seconds on large meshes.  Returns
 // false (with *err) when CUDA fails or the set is too small to bother (<= 2 * max_leaf_size triangles).

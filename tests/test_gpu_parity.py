@@ -574,17 +574,32 @@ def test_non_black_background_matches_oracle_and_both_kernels(gpu_rt, oracle):
 
 @pytest.mark.parametrize("name", ["practice7_2", "practice7_4"])
 def test_gpu_bvh_builder_gives_the_same_hits(gpu_rt, monkeypatch, name):
-    """the GPU LBVH builder (RT_BVH_BUILDER=gpu) replaces create_bvh_tree (bvh.rs:26-144).  Tree shape is
+    """the GPU LBVH builder (RT_BVH_BUILDER=gpu; the default for large meshes) replaces create_bvh_tree (bvh.rs:26-144).  Tree shape is
     not observable: the flattened tree must pass validate_bvh (bvh.rs:299-322 restated) and every primary ray must
     report the same triangle and distance as with the host SAH tree (f64 triangle tests: exact ties aside)."""
     W = H = 256
+    monkeypatch.setenv("RT_BVH_BUILDER", "host")
     host = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 16)
     monkeypatch.setenv("RT_BVH_BUILDER", "gpu")
     dev = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 16)
     monkeypatch.delenv("RT_BVH_BUILDER")
+    auto = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 16)            # default: GPU builder for meshes of >= 32 768 triangles
+    assert auto.info()["bvh_builder"] == (1 if name == "practice7_2" else 0)
+    auto.close()
     ih, idv = host.info(), dev.info()
     assert ih["bvh_builder"] == 0 and idv["bvh_builder"] == 1
     assert idv["bvh_validate_failures"] == 0 and idv["max_leaf_size"] <= 4 and idv["n_tris"] == ih["n_tris"]
+    if name == "practice7_2":                                            # the SAH rebuild of the top (regraft_top_sah) is on: fewer box tests than the host tree
+        monkeypatch.setenv("RT_BVH_BUILDER", "gpu"); monkeypatch.setenv("RT_BVH_TOP_SAH", "0")
+        morton = gpu_rt.Scene.from_gltf(scene_path(name), 96, 96, 8)
+        monkeypatch.delenv("RT_BVH_BUILDER"); monkeypatch.delenv("RT_BVH_TOP_SAH")
+        dev.set_frame(96, 96, 8)
+        _, s_m = morton.render_linear(seed=4, collect_stats=True)
+        _, s_r = dev.render_linear(seed=4, collect_stats=True)
+        dev.set_frame(W, H, 16)
+        assert s_r["node_tests"] < 0.85 * s_m["node_tests"], (s_r["node_tests"], s_m["node_tests"])
+        assert morton.info()["bvh_validate_failures"] == 0
+        morton.close()
     xs, ys = np.meshgrid(np.arange(W), np.arange(H))
     xy = np.stack([xs.ravel(), ys.ravel()], axis=1).astype(np.int32)
     rays = host.primary_rays(xy, np.full((xy.shape[0], 2), 0.5))
