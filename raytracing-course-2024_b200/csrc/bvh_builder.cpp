@@ -84,6 +84,59 @@ struct Build {
         return self;
     }
 
+    // Bottom-up alternative for SMALL sets (O(n^3), n <= 512): greedy agglomerative clustering -- merge the two clusters whose union has the
+    // smallest surface area (Walter et al. 2008) -- then the optimal leaf / inner decision per node by dynamic programming over the
+    // same cost model as the sweep (leaf: count * area; inner: traversal_cost * area + children).  Fills `nodes` (pre-order) and `order`.
+    void build_agglomerative(int* max_depth) {
+        struct A { Box box; int left, right, count, prim; double cost; bool leaf; };
+        const int n = (int)order.size();
+        std::vector<A> t;
+        std::vector<int> active;
+        for (int i = 0; i < n; ++i) { A a; a.box = boxes[(size_t)order[(size_t)i]]; a.left = a.right = -1; a.count = 1; a.prim = order[(size_t)i]; a.cost = a.box.half_area(); a.leaf = true; t.push_back(a); active.push_back(i); }
+        while (active.size() > 1) {
+            double best = kInf; size_t bi = 0, bj = 1;
+            for (size_t i = 0; i < active.size(); ++i)
+                for (size_t j = i + 1; j < active.size(); ++j) {
+                    Box u = t[(size_t)active[i]].box; u.grow(t[(size_t)active[j]].box);
+                    const double a = u.half_area();                       // (the increase of area, or area x count, measured worse: DESIGN.md section 13)
+                    if (a < best) { best = a; bi = i; bj = j; }
+                }
+            A m; m.box = t[(size_t)active[bi]].box; m.box.grow(t[(size_t)active[bj]].box);
+            m.left = active[bi]; m.right = active[bj]; m.count = t[(size_t)m.left].count + t[(size_t)m.right].count; m.prim = -1;
+            const double area = m.box.half_area();
+            const double inner = p.traversal_cost * area + t[(size_t)m.left].cost + t[(size_t)m.right].cost;
+            const double as_leaf = (double)m.count * area;
+            m.leaf = m.count <= p.max_leaf_size && m.count <= 8 && as_leaf <= inner;
+            m.cost = m.leaf ? as_leaf : inner;
+            t.push_back(m);
+            active[bi] = (int)t.size() - 1;
+            active.erase(active.begin() + (long)bj);
+        }
+        // pre-order emission into TempNode / order
+        nodes.clear();
+        std::vector<int32_t> new_order;
+        struct It { int a, parent, side, depth; };
+        std::vector<It> st(1, It{active[0], -1, 0, 1});
+        while (!st.empty()) {
+            const It it = st.back(); st.pop_back();
+            const A& a = t[(size_t)it.a];
+            TempNode nd; nd.box = a.box; nd.count = a.count; nd.first = (int)new_order.size();
+            *max_depth = std::max(*max_depth, it.depth);
+            const int self = (int)nodes.size();
+            nodes.push_back(nd);
+            if (it.parent >= 0) { if (it.side == 0) nodes[(size_t)it.parent].left = self; else nodes[(size_t)it.parent].right = self; }
+            if (a.leaf) {                                  // gather the primitives below in depth-first order
+                std::vector<int> g(1, it.a);
+                while (!g.empty()) { const int x = g.back(); g.pop_back(); if (t[(size_t)x].prim >= 0) new_order.push_back(t[(size_t)x].prim); else { g.push_back(t[(size_t)x].right); g.push_back(t[(size_t)x].left); } }
+            } else {
+                // `first` of an inner node = where its left-most primitive will land: the left child is emitted next (stack order), so the running size is right
+                st.push_back(It{a.right, self, 1, it.depth + 1});
+                st.push_back(It{a.left, self, 0, it.depth + 1});
+            }
+        }
+        order = new_order;
+    }
+
     void sort_axis(int first, int count, int axis) {
         std::sort(order.begin() + first, order.begin() + first + count, [this, axis](int32_t x, int32_t y) {
             double cx = boxes[(size_t)x].mn[axis] + boxes[(size_t)x].mx[axis], cy = boxes[(size_t)y].mn[axis] + boxes[(size_t)y].mx[axis];
@@ -145,7 +198,8 @@ void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, 
     b.boxes.resize((size_t)(max_id + 1));
     for (int32_t id : ids) b.boxes[(size_t)id] = from_d(boxes[(size_t)id]);
     int max_depth = 0;
-    if (!ids.empty()) b.build(0, (int)ids.size(), 1, &max_depth);
+    if (p.agglomerative && ids.size() >= 2 && ids.size() <= 512) b.build_agglomerative(&max_depth);
+    else if (!ids.empty()) b.build(0, (int)ids.size(), 1, &max_depth);
     out->tri_order = b.order;
     out->depth = max_depth;
     if (!ids.empty() && b.nodes[0].left >= 0) {

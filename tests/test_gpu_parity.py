@@ -589,15 +589,15 @@ def test_gpu_bvh_builder_gives_the_same_hits(gpu_rt, monkeypatch, name):
     ih, idv = host.info(), dev.info()
     assert ih["bvh_builder"] == 0 and idv["bvh_builder"] == 1
     assert idv["bvh_validate_failures"] == 0 and idv["max_leaf_size"] <= 4 and idv["n_tris"] == ih["n_tris"]
-    if name == "practice7_2":                                            # the SAH rebuild of the top (regraft_top_sah) is on: fewer box tests than the host tree
-        monkeypatch.setenv("RT_BVH_BUILDER", "gpu"); monkeypatch.setenv("RT_BVH_TOP_SAH", "0")
+    if name == "practice7_2":                                            # the rebuild of the top (regraft_top_sah, twice) is on: far fewer box tests than the bare Morton tree
+        monkeypatch.setenv("RT_BVH_BUILDER", "gpu"); monkeypatch.setenv("RT_BVH_TOP_SAH", "0"); monkeypatch.setenv("RT_BVH_TOP_AGGLO", "0")
         morton = gpu_rt.Scene.from_gltf(scene_path(name), 96, 96, 8)
-        monkeypatch.delenv("RT_BVH_BUILDER"); monkeypatch.delenv("RT_BVH_TOP_SAH")
+        monkeypatch.delenv("RT_BVH_BUILDER"); monkeypatch.delenv("RT_BVH_TOP_SAH"); monkeypatch.delenv("RT_BVH_TOP_AGGLO")
         dev.set_frame(96, 96, 8)
         _, s_m = morton.render_linear(seed=4, collect_stats=True)
         _, s_r = dev.render_linear(seed=4, collect_stats=True)
         dev.set_frame(W, H, 16)
-        assert s_r["node_tests"] < 0.85 * s_m["node_tests"], (s_r["node_tests"], s_m["node_tests"])
+        assert s_r["node_tests"] < 0.80 * s_m["node_tests"], (s_r["node_tests"], s_m["node_tests"])
         assert morton.info()["bvh_validate_failures"] == 0
         morton.close()
     xs, ys = np.meshgrid(np.arange(W), np.arange(H))
