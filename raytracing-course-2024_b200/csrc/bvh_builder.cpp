@@ -112,11 +112,80 @@ struct Build {
             active[bi] = (int)t.size() - 1;
             active.erase(active.begin() + (long)bj);
         }
+        int root = active[0];
+        // Re-insertion (Bittner, Hapala, Havran 2013): take a subtree out, close the gap with its sibling, and put it back where the sum
+        // of the inner-node areas grows least (the old place is among the candidates, so a step never makes the tree worse); repeated
+        // over all nodes, largest area first, until a pass gains < 0.1 %.  Brute-force candidate search: these sets are small.
+        if (p.reinsertion && n >= 4) {
+            std::vector<int> parent(t.size(), -1);
+            for (size_t i = 0; i < t.size(); ++i) if (t[i].prim < 0) { parent[(size_t)t[i].left] = (int)i; parent[(size_t)t[i].right] = (int)i; }
+            auto refit_up = [&](int x) {
+                for (; x >= 0; x = parent[(size_t)x]) {
+                    A& a = t[(size_t)x];
+                    a.box = t[(size_t)a.left].box; a.box.grow(t[(size_t)a.right].box);
+                    a.count = t[(size_t)a.left].count + t[(size_t)a.right].count;
+                }
+            };
+            auto total_area = [&]() { double c = 0.0; for (size_t i = 0; i < t.size(); ++i) if (t[i].prim < 0) c += t[i].box.half_area(); return c; };
+            double before = total_area();
+            for (int pass = 0; pass < 24; ++pass) {
+                std::vector<int> cand;
+                for (size_t i = 0; i < t.size(); ++i) if ((int)i != root && parent[i] >= 0) cand.push_back((int)i);
+                std::sort(cand.begin(), cand.end(), [&](int x, int y) { const double ax = t[(size_t)x].box.half_area(), ay = t[(size_t)y].box.half_area(); return ax != ay ? ax > ay : x < y; });
+                for (int sidx : cand) {
+                    const int pnode = parent[(size_t)sidx];
+                    if (pnode < 0) continue;
+                    const int sib = t[(size_t)pnode].left == sidx ? t[(size_t)pnode].right : t[(size_t)pnode].left;
+                    const int g = parent[(size_t)pnode];
+                    // detach: sib takes the place of pnode
+                    parent[(size_t)sib] = g;
+                    if (g < 0) root = sib; else { if (t[(size_t)g].left == pnode) t[(size_t)g].left = sib; else t[(size_t)g].right = sib; refit_up(g); }
+                    parent[(size_t)sidx] = -1; parent[(size_t)pnode] = -1;
+                    // best position: every node x of the remaining tree
+                    const Box sb = t[(size_t)sidx].box;
+                    double best = kInf; int bx = -1;
+                    std::vector<std::pair<int, double>> stck(1, std::make_pair(root, 0.0));      // (node, area increase induced in its ancestors)
+                    while (!stck.empty()) {
+                        const std::pair<int, double> it = stck.back(); stck.pop_back();
+                        const A& x = t[(size_t)it.first];
+                        Box u = x.box; u.grow(sb);
+                        const double direct = u.half_area();
+                        if (it.second + direct < best) { best = it.second + direct; bx = it.first; }
+                        if (x.prim < 0) {
+                            const double induced = it.second + direct - x.box.half_area();
+                            if (induced < best) { stck.push_back(std::make_pair(x.left, induced)); stck.push_back(std::make_pair(x.right, induced)); }   // branch and bound
+                        }
+                    }
+                    // insert: pnode becomes the parent of (bx, sidx) in bx's place
+                    const int bp = parent[(size_t)bx];
+                    t[(size_t)pnode].left = bx; t[(size_t)pnode].right = sidx;
+                    parent[(size_t)bx] = pnode; parent[(size_t)sidx] = pnode; parent[(size_t)pnode] = bp;
+                    if (bp < 0) root = pnode; else { if (t[(size_t)bp].left == bx) t[(size_t)bp].left = pnode; else t[(size_t)bp].right = pnode; }
+                    refit_up(pnode);
+                }
+                const double after = total_area();
+                if (!(after < before * 0.999)) break;
+                before = after;
+            }
+            // leaf / inner decision again, bottom-up
+            std::vector<std::pair<int, int>> po(1, std::make_pair(root, 0));
+            while (!po.empty()) {
+                const int x = po.back().first;
+                A& a = t[(size_t)x];
+                if (a.prim >= 0) { po.pop_back(); continue; }
+                if (po.back().second == 0) { po.back().second = 1; const int l = a.left, r = a.right; po.push_back(std::make_pair(l, 0)); po.push_back(std::make_pair(r, 0)); continue; }
+                const double area = a.box.half_area();
+                const double inner = p.traversal_cost * area + t[(size_t)a.left].cost + t[(size_t)a.right].cost, as_leaf = (double)a.count * area;
+                a.leaf = a.count <= p.max_leaf_size && a.count <= 8 && as_leaf <= inner;
+                a.cost = a.leaf ? as_leaf : inner;
+                po.pop_back();
+            }
+        }
         // pre-order emission into TempNode / order
         nodes.clear();
         std::vector<int32_t> new_order;
         struct It { int a, parent, side, depth; };
-        std::vector<It> st(1, It{active[0], -1, 0, 1});
+        std::vector<It> st(1, It{root, -1, 0, 1});
         while (!st.empty()) {
             const It it = st.back(); st.pop_back();
             const A& a = t[(size_t)it.a];

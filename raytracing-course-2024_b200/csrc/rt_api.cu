@@ -276,6 +276,7 @@ int flatten_scene(RtScene* s) {
     // 2 triangle tests give the fastest trees; the reference's own limit is 4 (bvh.rs:89)
     bp.max_leaf_size = env_int("RT_BVH_MAX_LEAF", 2);
     bp.traversal_cost = env_double("RT_BVH_TRAV_COST", 2.0);
+    bp.reinsertion = env_int("RT_BVH_REINSERT", 1) != 0;   // + subtree re-insertion passes (+0.5..2 %)
     bp.agglomerative = env_int("RT_BVH_AGGLO", 1) != 0;   // sets of <= 512 primitives: bottom-up clustering (measured +4.7 % on practice7_4 over the sweep)
     if (bp.max_leaf_size < 1) bp.max_leaf_size = 1;
     if (bp.max_leaf_size > 8) bp.max_leaf_size = 8;
@@ -289,12 +290,13 @@ int flatten_scene(RtScene* s) {
     const int n = (int)all.size(), n_planes = (int)s->plane_ids.size();
     std::vector<rtb::BoxD> boxes((size_t)n_all);
     for (int32_t id : all) boxes[(size_t)id] = object_box(h, id);
-    // builder (RT_BVH_BUILDER = host | gpu | auto, default auto): the host's full-sweep SAH for small scenes, and for triangle meshes of
-    // >= RT_BVH_GPU_MIN_TRIS (32 768) triangles the GPU LBVH (leaves <= 2) whose top is rebuilt with the SAH sweep over ~8 192 subtrees
-    // (regraft_top_sah) -- measured on practice7_2 / 7_3: 27 ms instead of 623 / 426 ms, and 1 330 / 1 130 instead of 1 311 / 1 112
-    // Msamples/s.  Host-only scenes, general-primitive scenes and CUDA failures take the host builder.
+    // builder (RT_BVH_BUILDER = host | gpu | auto, default auto).  host: bottom-up clustering + re-insertion for sets of <= 512 primitives,
+    // else the full-sweep SAH whose top (the 128 largest subtrees) is rebuilt bottom-up -- the best trees (practice7_2: 1 524 Msamples/s)
+    // after 0.6 s of building.  gpu: Morton-code LBVH (leaves <= 2) whose top is rebuilt twice on the host (SAH sweep over ~8 192 subtrees,
+    // then bottom-up over 128): 1 481 Msamples/s after 35 ms.  auto = host below RT_BVH_GPU_MIN_TRIS (1 000 000) triangles, where the
+    // host's O(n log^2 n) stays within seconds.  Host-only scenes, general-primitive scenes and CUDA failures take the host builder.
     const char* which = std::getenv("RT_BVH_BUILDER");
-    const bool want_gpu = which && *which && std::strcmp(which, "auto") != 0 ? std::strcmp(which, "gpu") == 0 : n >= env_int("RT_BVH_GPU_MIN_TRIS", 32768);
+    const bool want_gpu = which && *which && std::strcmp(which, "auto") != 0 ? std::strcmp(which, "gpu") == 0 : n >= env_int("RT_BVH_GPU_MIN_TRIS", 1000000);
     s->bvh_builder = 0; s->bvh_build_ms = 0.0;
     bool built = false;
     if (want_gpu && s->device >= 0 && !gen) {
@@ -312,6 +314,9 @@ int flatten_scene(RtScene* s) {
     if (!built) {
         const auto t0 = std::chrono::steady_clock::now();
         rtb::build_bvh(boxes, all, bp, &s->bvh);
+        // triangle meshes too big for the bottom-up builder get it for the TOP of their tree (the 128 largest subtrees): practice7_2 1 312 ->
+        // 1 523 Msamples/s.  Not for general-primitive scenes: the heavily overlapping boxes / ellipsoids of working.txt lose 4 % with it.
+        if (!gen && n > 512 && env_int("RT_BVH_TOP_AGGLO", 128) > 0) rtb::regraft_top_sah(&s->bvh, std::min(512, env_int("RT_BVH_TOP_AGGLO", 128)), bp);
         s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
     s->validate_failures = rtb::validate_flat_bvh(s->bvh, boxes);

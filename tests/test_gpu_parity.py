@@ -574,7 +574,7 @@ def test_non_black_background_matches_oracle_and_both_kernels(gpu_rt, oracle):
 
 @pytest.mark.parametrize("name", ["practice7_2", "practice7_4"])
 def test_gpu_bvh_builder_gives_the_same_hits(gpu_rt, monkeypatch, name):
-    """the GPU LBVH builder (RT_BVH_BUILDER=gpu; the default for large meshes) replaces create_bvh_tree (bvh.rs:26-144).  Tree shape is
+    """the GPU LBVH builder (RT_BVH_BUILDER=gpu; auto picks it for meshes of >= 1 000 000 triangles) replaces create_bvh_tree (bvh.rs:26-144).  Tree shape is
     not observable: the flattened tree must pass validate_bvh (bvh.rs:299-322 restated) and every primary ray must
     report the same triangle and distance as with the host SAH tree (f64 triangle tests: exact ties aside)."""
     W = H = 256
@@ -583,9 +583,11 @@ def test_gpu_bvh_builder_gives_the_same_hits(gpu_rt, monkeypatch, name):
     monkeypatch.setenv("RT_BVH_BUILDER", "gpu")
     dev = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 16)
     monkeypatch.delenv("RT_BVH_BUILDER")
-    auto = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 16)            # default: GPU builder for meshes of >= 32 768 triangles
+    monkeypatch.setenv("RT_BVH_GPU_MIN_TRIS", "32768")                   # auto: the GPU builder from this many triangles on (default 1 000 000)
+    auto = gpu_rt.Scene.from_gltf(scene_path(name), W, H, 16)
     assert auto.info()["bvh_builder"] == (1 if name == "practice7_2" else 0)
     auto.close()
+    monkeypatch.delenv("RT_BVH_GPU_MIN_TRIS")
     ih, idv = host.info(), dev.info()
     assert ih["bvh_builder"] == 0 and idv["bvh_builder"] == 1
     assert idv["bvh_validate_failures"] == 0 and idv["max_leaf_size"] <= 4 and idv["n_tris"] == ih["n_tris"]
