@@ -154,6 +154,66 @@ def test_quantised_nodes_enclose_the_full_precision_nodes(rt, name):
     sc.close(); small.close()
 
 
+def _tree_stats(sc):
+    """(sum of the half-areas of the inner-node boxes, sorted leaf codes, set of triangles in the leaves) of a scene's flattened tree."""
+    nodes, order = sc.bvh()
+    lo = nodes[:, [0, 1, 2, 6, 7, 8]].reshape(-1, 2, 3).astype(np.float64)
+    hi = nodes[:, [3, 4, 5, 9, 10, 11]].reshape(-1, 2, 3).astype(np.float64)
+    ext = hi - lo
+    area = ext[..., 0] * ext[..., 1] + ext[..., 1] * ext[..., 2] + ext[..., 2] * ext[..., 0]
+    refs = nodes[:, 12:14].astype(np.int64)
+    inner = refs >= 0
+    leaves = np.sort(refs[~inner])
+    tris = []
+    for code in (~leaves).tolist():
+        tris += list(range(code >> 3, (code >> 3) + (code & 7) + 1))
+    return float(area[inner].sum()), float(area.sum()), leaves, sorted(order[tris].tolist())
+
+
+@pytest.mark.parametrize("name", ["practice7_1", "practice7_4"])
+def test_bottom_up_builder_gives_a_valid_tree_of_lower_cost(rt, name, monkeypatch):
+    """Sets of <= 512 primitives are built bottom-up (greedy clustering by the area of the union + re-insertion, bvh_builder.cpp)
+    instead of by the top-down SAH sweep (RT_BVH_AGGLO=0).  Both trees must hold every triangle exactly once and pass the
+    containment check of bvh.rs:299-322; the bottom-up one must be cheaper under the surface-area cost both builders minimise."""
+    monkeypatch.setenv("RT_BVH_AGGLO", "0")
+    sweep = rt.Scene.from_gltf(scene_path(name), 8, 8, 1, device=-1)
+    monkeypatch.delenv("RT_BVH_AGGLO")
+    bottom_up = rt.Scene.from_gltf(scene_path(name), 8, 8, 1, device=-1)
+    monkeypatch.setenv("RT_BVH_REINSERT", "0")
+    no_reinsert = rt.Scene.from_gltf(scene_path(name), 8, 8, 1, device=-1)
+    monkeypatch.delenv("RT_BVH_REINSERT")
+    n = sweep.info()["n_tris"]
+    stats = {}
+    for label, sc in (("sweep", sweep), ("bottom_up", bottom_up), ("no_reinsert", no_reinsert)):
+        info = sc.info()
+        assert info["bvh_validate_failures"] == 0 and info["max_leaf_size"] <= 2 and info["n_tris"] == n
+        inner_area, all_area, _, tris = _tree_stats(sc)
+        assert tris == list(range(n)), label                       # every triangle in exactly one leaf
+        stats[label] = all_area
+    assert stats["bottom_up"] <= stats["no_reinsert"] * (1 + 1e-9)     # re-insertion never makes the tree worse
+    assert stats["bottom_up"] < (0.95 if name == "practice7_4" else 1.0) * stats["sweep"], stats   # less box area than the sweep
+    for sc in (sweep, bottom_up, no_reinsert):
+        sc.close()
+
+
+def test_bottom_up_top_of_a_large_tree_keeps_the_leaves(rt, monkeypatch):
+    """regraft_top_sah (bvh_builder.cpp): the part of a large triangle mesh's tree above its 128 largest subtrees is rebuilt bottom-up
+    and the subtrees are grafted back.  Same node count, same leaves, valid containment, less box area near the root."""
+    monkeypatch.setenv("RT_BVH_TOP_AGGLO", "0")
+    plain = rt.Scene.from_gltf(scene_path("practice7_3"), 8, 8, 1, device=-1)
+    monkeypatch.delenv("RT_BVH_TOP_AGGLO")
+    grafted = rt.Scene.from_gltf(scene_path("practice7_3"), 8, 8, 1, device=-1)
+    ip, ig = plain.info(), grafted.info()
+    assert ip["bvh_validate_failures"] == 0 and ig["bvh_validate_failures"] == 0
+    assert ip["n_nodes"] == ig["n_nodes"] and ip["n_leaves"] == ig["n_leaves"] and ip["bvh_builder"] == 0 and ig["bvh_builder"] == 0
+    _, area_p, leaves_p, tris_p = _tree_stats(plain)
+    _, area_g, leaves_g, tris_g = _tree_stats(grafted)
+    assert np.array_equal(leaves_p, leaves_g) and tris_p == tris_g == list(range(ip["n_tris"]))
+    assert area_g < area_p                                             # the rebuilt top is what every ray pays for
+    assert ig["bvh_depth"] <= ip["bvh_depth"] + 16
+    plain.close(); grafted.close()
+
+
 def test_host_only_scene_refuses_compute_and_reports_errors(rt, tmp_path):
     sc = rt.Scene.from_gltf(scene_path("practice7_1"), 8, 8, 1, device=-1)
     with pytest.raises(rt.RtError) as e:
