@@ -55,6 +55,16 @@ struct Build {
 
         double best_cost = kInf; int best_axis = -1, best_split = -1;
         right_area.resize((size_t)count);
+        if (p.force_median) {                              // balanced fallback: median of the centres along the longest axis, leaves of <= max_leaf
+            if (count <= p.max_leaf_size && count <= 8) return self;
+            int ax = 0;
+            for (int a = 1; a < 3; ++a) if (n.box.mx[a] - n.box.mn[a] > n.box.mx[ax] - n.box.mn[ax]) ax = a;
+            sort_axis(first, count, ax);
+            int l = build(first, count / 2, depth + 1, max_depth);
+            int r = build(first + count / 2, count - count / 2, depth + 1, max_depth);
+            nodes[(size_t)self].left = l; nodes[(size_t)self].right = r;
+            return self;
+        }
         for (int axis = 0; axis < 3; ++axis) {
             sort_axis(first, count, axis);
             Box acc; acc.reset();
@@ -156,6 +166,7 @@ struct Build {
                             if (induced < best) { stck.push_back(std::make_pair(x.left, induced)); stck.push_back(std::make_pair(x.right, induced)); }   // branch and bound
                         }
                     }
+                    if (bx < 0) bx = root;                                                         // (cannot happen with finite boxes)
                     // insert: pnode becomes the parent of (bx, sidx) in bx's place
                     const int bp = parent[(size_t)bx];
                     t[(size_t)pnode].left = bx; t[(size_t)pnode].right = sidx;
@@ -265,9 +276,15 @@ void build_bvh(const std::vector<BoxD>& boxes, const std::vector<int32_t>& ids, 
     int32_t max_id = -1;
     for (int32_t id : ids) max_id = std::max(max_id, id);
     b.boxes.resize((size_t)(max_id + 1));
-    for (int32_t id : ids) b.boxes[(size_t)id] = from_d(boxes[(size_t)id]);
+    for (int32_t id : ids) {
+        Box bx = from_d(boxes[(size_t)id]);
+        bool finite = true;                                   // a primitive with NaN / inf / astronomically large coordinates cannot be hit; it must not poison
+        for (int a = 0; a < 3; ++a) finite = finite && std::isfinite(bx.mn[a]) && std::isfinite(bx.mx[a]) && std::fabs(bx.mn[a]) < 1e30 && std::fabs(bx.mx[a]) < 1e30;   // the comparisons of the builders
+        if (!finite) for (int a = 0; a < 3; ++a) { bx.mn[a] = 0.0; bx.mx[a] = 0.0; }
+        b.boxes[(size_t)id] = bx;
+    }
     int max_depth = 0;
-    if (p.agglomerative && ids.size() >= 2 && ids.size() <= 512) b.build_agglomerative(&max_depth);
+    if (p.agglomerative && !p.force_median && ids.size() >= 2 && ids.size() <= 512) b.build_agglomerative(&max_depth);
     else if (!ids.empty()) b.build(0, (int)ids.size(), 1, &max_depth);
     out->tri_order = b.order;
     out->depth = max_depth;
@@ -327,6 +344,7 @@ void regraft_top_sah(FlatBvh* bvh, int n_clusters, const BvhBuildParams& p) {
         Elem e; e.box = slot_box(node, s); e.ref = bvh->child[(size_t)node * 2 + (size_t)s];
         const double x = e.box.mx[0] - e.box.mn[0], y = e.box.mx[1] - e.box.mn[1], z = e.box.mx[2] - e.box.mn[2];
         e.area = x * y + y * z + z * x;
+        if (!(e.area >= 0.0)) e.area = 0.0;                   // NaN boxes (non-finite input) must not break the heap order
         return e;
     };
     std::vector<Elem> done;                                   // leaves met on the way: part of the frontier as they are

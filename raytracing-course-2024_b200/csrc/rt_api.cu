@@ -319,6 +319,11 @@ int flatten_scene(RtScene* s) {
         if (!gen && n > 512 && env_int("RT_BVH_TOP_AGGLO", 128) > 0) rtb::regraft_top_sah(&s->bvh, std::min(512, env_int("RT_BVH_TOP_AGGLO", 128)), bp);
         s->bvh_build_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count();
     }
+    if (s->bvh.depth + 3 > 80) {                               // degenerate input (hundreds of coincident primitives make every split cost the same and
+        rtb::BvhBuildParams mp = bp; mp.force_median = true;   // the trees chain-shaped): fall back to median splits, depth <= log2(n) + 2
+        rtb::build_bvh(boxes, all, mp, &s->bvh);
+        s->bvh_builder = 0;
+    }
     s->validate_failures = rtb::validate_flat_bvh(s->bvh, boxes);
 
     // lights: emission.norm() > EPS (gltf_to_scene.rs:240), finite primitives only

@@ -214,6 +214,37 @@ def test_bottom_up_top_of_a_large_tree_keeps_the_leaves(rt, monkeypatch):
     plain.close(); grafted.close()
 
 
+@pytest.mark.parametrize("n,poison", [(300, "nan"), (300, "huge"), (300, "same"), (3000, "nan"), (3000, "halfsame"), (3, "nan"), (513, "none")])
+def test_builders_survive_degenerate_geometry(rt, n, poison):
+    """Non-finite or astronomically large vertices must not hang or crash the builders (their boxes are parked at the origin: such a
+    triangle cannot be hit anyway), and hundreds of coincident triangles -- every split costs the same, the cost-driven trees become
+    chains deeper than the traversal stack -- fall back to median splits instead of failing with RT_ERR_LIMIT."""
+    rng = np.random.default_rng(0)
+    c = rng.uniform(-5, 5, (n, 1, 3))
+    v = (c + rng.normal(0, 0.2, (n, 3, 3))).reshape(n, 9)
+    if poison == "nan":
+        v[min(5, n - 1), 2] = np.nan; v[min(100, n - 1), 7] = np.inf
+    if poison == "huge":
+        v[7] *= 1e35
+    if poison == "same":
+        v[:] = v[0]
+    if poison == "halfsame":
+        v[: n // 2] = v[0]
+    sc = rt.Scene.from_arrays(width=16, height=16, samples=1, ray_depth=3, bg_color=[0, 0, 0], camera_position=[0, 0, 20], camera_forward=[0, 0, -1],
+                              camera_right=[1, 0, 0], camera_up=[0, 1, 0], camera_fov_x=1.0, camera_fov_y=1.0, tri_v=v, tri_n=np.tile([0, 0, 1.0], (n, 3)).reshape(n, 9),
+                              tri_material=np.tile([0.8, 0.8, 0.8, 0, 1.0], (n, 1)), tri_emission=np.zeros((n, 3)), device=-1)
+    info = sc.info()
+    assert info["n_tris"] == n and info["max_leaf_size"] <= 2
+    assert info["bvh_depth"] <= 40, info["bvh_depth"]                    # (coincident triangles: median fallback, depth ~ log2 n)
+    _, order = sc.bvh()
+    assert sorted(order.tolist()) == list(range(n))
+    if poison in ("none", "same", "halfsame"):
+        assert info["bvh_validate_failures"] == 0
+    else:
+        assert info["bvh_validate_failures"] <= 2                          # only the poisoned triangles are outside their (parked) boxes
+    sc.close()
+
+
 def test_host_only_scene_refuses_compute_and_reports_errors(rt, tmp_path):
     sc = rt.Scene.from_gltf(scene_path("practice7_1"), 8, 8, 1, device=-1)
     with pytest.raises(rt.RtError) as e:
