@@ -65,7 +65,7 @@ struct Build {
             nodes[(size_t)self].left = l; nodes[(size_t)self].right = r;
             return self;
         }
-        for (int axis = 0; axis < 3; ++axis) {
+        for (int axis = 0; axis < (p.size_split ? 4 : 3); ++axis) {             // axis 3: primitives ordered by box area, largest first ("the walls vs the mesh")
             sort_axis(first, count, axis);
             Box acc; acc.reset();
             for (int i = count - 1; i > 0; --i) { acc.grow(boxes[(size_t)order[(size_t)(first + i)]]); right_area[(size_t)i] = acc.half_area(); }
@@ -218,6 +218,14 @@ struct Build {
     }
 
     void sort_axis(int first, int count, int axis) {
+        if (axis == 3) {
+            std::sort(order.begin() + first, order.begin() + first + count, [this](int32_t x, int32_t y) {
+                const double ax = boxes[(size_t)x].half_area(), ay = boxes[(size_t)y].half_area();
+                if (ax != ay) return ax > ay;
+                return x < y;
+            });
+            return;
+        }
         std::sort(order.begin() + first, order.begin() + first + count, [this, axis](int32_t x, int32_t y) {
             double cx = boxes[(size_t)x].mn[axis] + boxes[(size_t)x].mx[axis], cy = boxes[(size_t)y].mn[axis] + boxes[(size_t)y].mx[axis];
             if (cx != cy) return cx < cy;

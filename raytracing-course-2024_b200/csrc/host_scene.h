@@ -62,6 +62,7 @@ BoxD tri_box_d(const double* v9);
 struct BvhBuildParams {
     int max_leaf_size = 4;       // bvh.rs:89 (n <= 4 never splits)
     double traversal_cost = 1.0; // cost of one box test relative to one triangle test in the SAH
+    bool size_split = false;     // experiment: the sweep also tries the order by box area (largest first) as a fourth axis
     bool force_median = false;   // object-median splits on the longest axis instead of any cost heuristic (fallback for degenerate input)
     bool reinsertion = true;     // (with agglomerative) subtree re-insertion passes after the clustering
     bool agglomerative = true;   // sets of <= 512 primitives: greedy bottom-up clustering instead of the top-down sweep (bvh_builder.cpp)

@@ -277,6 +277,7 @@ int flatten_scene(RtScene* s) {
     bp.max_leaf_size = env_int("RT_BVH_MAX_LEAF", 2);
     bp.traversal_cost = env_double("RT_BVH_TRAV_COST", 2.0);
     bp.reinsertion = env_int("RT_BVH_REINSERT", 1) != 0;   // + subtree re-insertion passes (+0.5..2 %)
+    bp.size_split = !gen && env_int("RT_BVH_SIZE_SPLIT", 1) != 0;   // triangle meshes: the sweep also tries "the k largest primitives | the rest" (walls vs the mesh inside)
     bp.agglomerative = env_int("RT_BVH_AGGLO", 1) != 0;   // sets of <= 512 primitives: bottom-up clustering (measured +4.7 % on practice7_4 over the sweep)
     if (bp.max_leaf_size < 1) bp.max_leaf_size = 1;
     if (bp.max_leaf_size > 8) bp.max_leaf_size = 8;

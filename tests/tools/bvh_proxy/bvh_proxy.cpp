@@ -83,5 +83,9 @@ int main(int argc, char** argv) {
     { BvhBuildParams q = p; q.agglomerative = false; FlatBvh b; build_bvh(boxes, ids, q, &b); report("top-down SAH sweep", b);
       if (n > 512) { for (int k : {8, 16, 32, 64, 96, 128, 192, 256, 512}) { FlatBvh t = b; regraft_top_sah(&t, k, p); char l[64]; snprintf(l, sizeof l, "sweep + bottom-up top %d", k); report(l, t); } } }
     if (n <= 512) { FlatBvh b; build_bvh(boxes, ids, p, &b); report("bottom-up + re-insertion", b); BvhBuildParams q = p; q.reinsertion = false; FlatBvh c; build_bvh(boxes, ids, q, &c); report("bottom-up", c); }
+    if (n > 512) {
+        BvhBuildParams q = p; q.agglomerative = false; q.size_split = true; FlatBvh b; build_bvh(boxes, ids, q, &b); report("sweep with the size order as 4th axis", b);
+        FlatBvh t = b; regraft_top_sah(&t, 128, p); report("  + bottom-up top 128", t);
+    }
     return 0;
 }
