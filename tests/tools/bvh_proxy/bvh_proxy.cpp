@@ -83,6 +83,56 @@ int main(int argc, char** argv) {
     { BvhBuildParams q = p; q.agglomerative = false; FlatBvh b; build_bvh(boxes, ids, q, &b); report("top-down SAH sweep", b);
       if (n > 512) { for (int k : {8, 16, 32, 64, 96, 128, 192, 256, 512}) { FlatBvh t = b; regraft_top_sah(&t, k, p); char l[64]; snprintf(l, sizeof l, "sweep + bottom-up top %d", k); report(l, t); } } }
     if (n <= 512) { FlatBvh b; build_bvh(boxes, ids, p, &b); report("bottom-up + re-insertion", b); BvhBuildParams q = p; q.reinsertion = false; FlatBvh c; build_bvh(boxes, ids, q, &c); report("bottom-up", c); }
+    if (argc > 3 && std::strcmp(argv[3], "search") == 0 && n <= 512) {
+        // How far is the library's tree from a LOCAL optimum of the measured work itself?  Hill climbing over subtree swaps (two child slots that are
+        // not on one root path exchange their contents, the boxes above are refitted), objective = box tests + 2.1 * triangle tests on a ray sample.
+        FlatBvh b; build_bvh(boxes, ids, p, &b);
+        const size_t n_eval = std::min<size_t>(ro.size(), 6000);
+        auto cost = [&](const FlatBvh& t, double* bx, double* tr) { Counts c; for (size_t k = 0; k < n_eval; ++k) walk(t, h.tri_v, ro[k], rd[k], c); if (bx) *bx = c.box / c.rays; if (tr) *tr = c.tri / c.rays; return (c.box + 2.1 * c.tri) / c.rays; };
+        auto get = [&](FlatBvh& t, int node, int s, float* bx6, int32_t* ref) {
+            const float* xy = s == 0 ? &t.box_a[(size_t)node * 4] : &t.box_b[(size_t)node * 4];
+            bx6[0] = xy[0]; bx6[1] = xy[1]; bx6[2] = xy[2]; bx6[3] = xy[3]; bx6[4] = t.box_c[(size_t)node * 4 + s * 2]; bx6[5] = t.box_c[(size_t)node * 4 + s * 2 + 1]; *ref = t.child[(size_t)node * 2 + s]; };
+        auto put = [&](FlatBvh& t, int node, int s, const float* bx6, int32_t ref) {
+            float* xy = s == 0 ? &t.box_a[(size_t)node * 4] : &t.box_b[(size_t)node * 4];
+            xy[0] = bx6[0]; xy[1] = bx6[1]; xy[2] = bx6[2]; xy[3] = bx6[3]; t.box_c[(size_t)node * 4 + s * 2] = bx6[4]; t.box_c[(size_t)node * 4 + s * 2 + 1] = bx6[5]; t.child[(size_t)node * 2 + s] = ref; };
+        auto parents = [&](const FlatBvh& t, std::vector<int>& par, std::vector<int>& side) {
+            par.assign((size_t)t.n_nodes, -1); side.assign((size_t)t.n_nodes, 0);
+            for (int i = 0; i < t.n_nodes; ++i) for (int s = 0; s < 2; ++s) { const int32_t r = t.child[(size_t)i * 2 + s]; if (r >= 0) { par[(size_t)r] = i; side[(size_t)r] = s; } } };
+        auto refit = [&](FlatBvh& t, int node, const std::vector<int>& par, const std::vector<int>& side) {
+            for (int x = node; par[(size_t)x] >= 0; x = par[(size_t)x]) {
+                float a6[6], b6[6], u[6]; int32_t r;
+                get(t, x, 0, a6, &r); get(t, x, 1, b6, &r);
+                for (int k = 0; k < 6; k += 2) { u[k] = std::min(a6[k], b6[k]); u[k + 1] = std::max(a6[k + 1], b6[k + 1]); }
+                put(t, par[(size_t)x], side[(size_t)x], u, x);
+            } };
+        double bx, tr; double best = cost(b, &bx, &tr);
+        printf("search start: cost %.3f (box %.3f, tri %.3f)\n", best, bx, tr);
+        std::mt19937_64 g2(11);
+        const int iters = argc > 4 ? atoi(argv[4]) : 60000;
+        int accepted = 0;
+        for (int it = 0; it < iters; ++it) {
+            std::vector<int> par, side; parents(b, par, side);
+            const int i = (int)(g2() % (uint64_t)b.n_nodes), j = (int)(g2() % (uint64_t)b.n_nodes), si = (int)(g2() & 1), sj = (int)((g2() >> 1) & 1);
+            if (i == j) continue;
+            // reject if one slot's subtree contains the other node (ancestor relation)
+            auto is_anc = [&](int anc_node, int anc_side, int x) { for (int y = x; par[(size_t)y] >= 0; y = par[(size_t)y]) if (par[(size_t)y] == anc_node && side[(size_t)y] == anc_side) return true; return false; };
+            if (is_anc(i, si, j) || is_anc(j, sj, i)) continue;
+            FlatBvh t = b;
+            float bi[6], bj[6]; int32_t ri, rj;
+            get(t, i, si, bi, &ri); get(t, j, sj, bj, &rj);
+            put(t, i, si, bj, rj); put(t, j, sj, bi, ri);
+            std::vector<int> par2, side2; parents(t, par2, side2);
+            refit(t, i, par2, side2); refit(t, j, par2, side2);
+            const double c2 = cost(t, nullptr, nullptr);
+            if (c2 < best) { best = c2; b = t; ++accepted; }
+        }
+        // honest evaluation on the FULL ray set (the search saw the first n_eval rays only)
+        Counts c; for (size_t k = n_eval; k < ro.size(); ++k) walk(b, h.tri_v, ro[k], rd[k], c);
+        printf("search end: %d swaps accepted, cost on the training rays %.3f; held-out rays: box %.3f tri %.3f; validate %d\n", accepted, best, c.box / c.rays, c.tri / c.rays, validate_flat_bvh(b, boxes));
+        FlatBvh b0; build_bvh(boxes, ids, p, &b0); Counts c0; for (size_t k = n_eval; k < ro.size(); ++k) walk(b0, h.tri_v, ro[k], rd[k], c0);
+        printf("library tree on the same held-out rays: box %.3f tri %.3f\n", c0.box / c0.rays, c0.tri / c0.rays);
+        return 0;
+    }
     if (n > 512) {
         BvhBuildParams q = p; q.agglomerative = false; q.size_split = true; FlatBvh b; build_bvh(boxes, ids, q, &b); report("sweep with the size order as 4th axis", b);
         FlatBvh t = b; regraft_top_sah(&t, 128, p); report("  + bottom-up top 128", t);
