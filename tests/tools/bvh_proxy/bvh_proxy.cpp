@@ -8,6 +8,7 @@
 #include <cstdlib>
 #include <cstring>
 #include <random>
+#include <array>
 #include "host_scene.h"
 using namespace rtb;
 struct V { double x, y, z; };
@@ -83,6 +84,42 @@ int main(int argc, char** argv) {
     { BvhBuildParams q = p; q.agglomerative = false; FlatBvh b; build_bvh(boxes, ids, q, &b); report("top-down SAH sweep", b);
       if (n > 512) { for (int k : {8, 16, 32, 64, 96, 128, 192, 256, 512}) { FlatBvh t = b; regraft_top_sah(&t, k, p); char l[64]; snprintf(l, sizeof l, "sweep + bottom-up top %d", k); report(l, t); } } }
     if (n <= 512) { FlatBvh b; build_bvh(boxes, ids, p, &b); report("bottom-up + re-insertion", b); BvhBuildParams q = p; q.reinsertion = false; FlatBvh c; build_bvh(boxes, ids, q, &c); report("bottom-up", c); }
+    if (argc > 3 && std::strcmp(argv[3], "split") == 0) {
+        // Potential of SPATIAL SPLITS: every triangle whose box area exceeds `frac` of the scene box is cut into 4^L sub-triangles by midpoint
+        // subdivision; each piece becomes a REFERENCE (its own box, the original triangle behind it).  The library's builders run over the references;
+        // the walk tests the original triangle (a triangle reached through two leaves is tested twice, as a real implementation would).
+        BoxD sb = boxes[0];
+        for (int i = 1; i < n; ++i) for (int a = 0; a < 3; ++a) { sb.mn[a] = std::min(sb.mn[a], boxes[(size_t)i].mn[a]); sb.mx[a] = std::max(sb.mx[a], boxes[(size_t)i].mx[a]); }
+        auto harea = [](const BoxD& b) { const double x = b.mx[0] - b.mn[0], y = b.mx[1] - b.mn[1], z = b.mx[2] - b.mn[2]; return x * y + y * z + z * x; };
+        const double scene_area = harea(sb);
+        for (double frac : {1.0, 0.05, 0.01, 0.002}) for (int L : {1, 2, 3}) {
+            if (frac == 1.0 && L > 1) continue;
+            std::vector<BoxD> rb; std::vector<int32_t> rtri; std::vector<double> rv;     // references: box, original triangle, vertices (for the f64 test)
+            for (int i = 0; i < n; ++i) {
+                std::vector<std::array<double, 9>> parts(1); for (int k = 0; k < 9; ++k) parts[0][(size_t)k] = h.tri_v[(size_t)i * 9 + (size_t)k];
+                if (harea(boxes[(size_t)i]) > frac * scene_area)
+                    for (int l = 0; l < L; ++l) {
+                        std::vector<std::array<double, 9>> nx;
+                        for (auto& t : parts) {
+                            double m[9]; for (int k = 0; k < 3; ++k) { m[k] = 0.5 * (t[(size_t)k] + t[(size_t)(3 + k)]); m[3 + k] = 0.5 * (t[(size_t)(3 + k)] + t[(size_t)(6 + k)]); m[6 + k] = 0.5 * (t[(size_t)(6 + k)] + t[(size_t)k]); }
+                            nx.push_back({t[0], t[1], t[2], m[0], m[1], m[2], m[6], m[7], m[8]}); nx.push_back({m[0], m[1], m[2], t[3], t[4], t[5], m[3], m[4], m[5]});
+                            nx.push_back({m[6], m[7], m[8], m[3], m[4], m[5], t[6], t[7], t[8]}); nx.push_back({m[0], m[1], m[2], m[3], m[4], m[5], m[6], m[7], m[8]});
+                        }
+                        parts.swap(nx);
+                    }
+                for (auto& t : parts) { rb.push_back(tri_box_d(t.data())); rtri.push_back(i); }
+            }
+            std::vector<int32_t> rid(rb.size()); for (size_t k = 0; k < rid.size(); ++k) rid[k] = (int32_t)k;
+            FlatBvh b; build_bvh(rb, rid, p, &b);
+            if ((int)rb.size() > 512) regraft_top_sah(&b, 128, p);
+            for (auto& x : b.tri_order) x = rtri[(size_t)x];                             // leaves now name original triangles
+            Counts c; for (size_t k = 0; k < ro.size(); ++k) walk(b, h.tri_v, ro[k], rd[k], c);
+            printf("split triangles above %5.3f of the scene box area, %d level(s): %6zu references (%d triangles), nodes %6d depth %3d  box tests / ray %7.3f  triangle tests / ray %6.3f\n",
+                   frac, L, rb.size(), n, b.n_nodes, b.depth, c.box / c.rays, c.tri / c.rays);
+            fflush(stdout);
+        }
+        return 0;
+    }
     if (argc > 3 && std::strcmp(argv[3], "search") == 0 && n <= 512) {
         // How far is the library's tree from a LOCAL optimum of the measured work itself?  Hill climbing over subtree swaps (two child slots that are
         // not on one root path exchange their contents, the boxes above are refitted), objective = box tests + 2.1 * triangle tests on a ray sample.
